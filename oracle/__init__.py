@@ -1,0 +1,5 @@
+"""CPU oracle of the hot path — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import anything from this package; the product (rl_arm_under_sparse_reward_b200) never does.
+"""

@@ -1,0 +1,621 @@
+// DDPG learner: actor/critic MLP forward + backward as cuBLASLt fp32 GEMMs (bias+ReLU fused
+// in the GEMM epilogue), fused loss / head / dReLU+bias-grad kernels, multi-tensor Adam on
+// flat parameter buffers, Polyak averaging.
+//
+// Reference behaviour restated (paths relative to the reference tree):
+//   models.py:11-44            actor / critic
+//   ddpg_agent.py:250-277      _update_network (targets, losses, two backward passes, Adam)
+//   ddpg_agent.py:220-222      _soft_update_target_network
+//   ddpg_agent.py:174-184      _select_actions
+//   utils.py:18-27             flat parameter order (named_parameters)
+//
+// Row-major convention: every activation is [rows][features]; torch Linear weights are
+// [out][in].  gemm_rm() maps C[M][N] = op(A) op(B) onto column-major cuBLASLt by swapping the
+// operands (C^T = op(B)^T op(A)^T), so a per-feature bias is a cuBLASLt row-bias epilogue.
+#include <cublasLt.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bmi {
+
+#define BMI_CUBLAS_CHECK(expr)                                                         \
+  do {                                                                                 \
+    cublasStatus_t _s = (expr);                                                        \
+    if (_s != CUBLAS_STATUS_SUCCESS) {                                                 \
+      ::bmi::set_error("%s:%d %s -> cublas status %d", __FILE__, __LINE__, #expr, (int)_s); \
+      return BMI_ERR_CUBLAS;                                                           \
+    }                                                                                  \
+  } while (0)
+
+struct GemmKey {
+  int opA, opB, M, N, K, lda, ldb, ldc, epi, alA, alB, alC;
+  bool operator<(const GemmKey& o) const {
+    return std::tie(opA, opB, M, N, K, lda, ldb, ldc, epi, alA, alB, alC) <
+           std::tie(o.opA, o.opB, o.M, o.N, o.K, o.lda, o.ldb, o.ldc, o.epi, o.alA, o.alB, o.alC);
+  }
+};
+
+// largest power of two (<= 256) dividing the base address (cuBLASLt sees the pitch itself)
+static inline int ptr_align(const void* p) {
+  uintptr_t v = (uintptr_t)p | 256u;
+  return (int)(v & (~v + 1));
+}
+
+struct GemmPlan {
+  cublasLtMatmulDesc_t desc = nullptr;
+  cublasLtMatrixLayout_t la = nullptr, lb = nullptr, lc = nullptr;
+  cublasLtMatmulAlgo_t algo;
+};
+
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_RELU_BIAS = 2 };
+
+// layer parameter offsets inside a flat buffer (named_parameters order)
+struct NetLayout {
+  int in_dim, hidden, out_dim;
+  int64_t w[4], b[4];
+  int64_t count;
+  void init(int in_d, int hid, int out_d) {
+    in_dim = in_d; hidden = hid; out_dim = out_d;
+    int ins[4] = {in_d, hid, hid, hid};
+    int outs[4] = {hid, hid, hid, out_d};
+    int64_t off = 0;
+    for (int l = 0; l < 4; ++l) {
+      w[l] = off; off += (int64_t)outs[l] * ins[l];
+      b[l] = off; off += outs[l];
+    }
+    count = off;
+  }
+  int fan_in(int l) const { return l == 0 ? in_dim : hidden; }
+  int fan_out(int l) const { return l == 3 ? out_dim : hidden; }
+};
+
+}  // namespace bmi
+
+using namespace bmi;
+
+struct bmi_ddpg {
+  bmi_ddpg_config cfg;
+  NetLayout la, lc;  // actor, critic
+  float *actor, *critic, *actor_t, *critic_t;  // caller-owned flat parameters
+  float* grads = nullptr;                       // [actor | pad to 64 floats | critic]
+  int64_t na_pad = 0, n_grads = 0;
+  float *adam_m = nullptr, *adam_v = nullptr;   // same layout as grads
+  int* adam_step = nullptr;                     // device step counter
+  float* adam_scal = nullptr;                   // [4] step_size_a, step_size_c, 1/sqrt(bc2), -
+  cublasLtHandle_t lt = nullptr;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 8u << 20;
+  std::map<GemmKey, GemmPlan> plans;
+  // training activations (batch rows)
+  float *xc = nullptr, *h1 = nullptr, *h2 = nullptr, *h3 = nullptr;        // scratch chain
+  float *ch1 = nullptr, *ch2 = nullptr, *ch3 = nullptr, *q = nullptr;      // critic(x, A)
+  float *ah1 = nullptr, *ah2 = nullptr, *ah3 = nullptr, *az = nullptr, *aa = nullptr;  // actor(x)
+  float *qh1 = nullptr, *qh2 = nullptr, *qh3 = nullptr, *qa = nullptr, *xca = nullptr; // critic(x, pi(x))
+  float *a_next = nullptr, *q_next = nullptr, *y = nullptr;
+  float *d1 = nullptr, *d2 = nullptr, *dq = nullptr, *dxc = nullptr, *dz = nullptr;    // backward scratch
+  // policy (act) activations (max_act_rows)
+  float *ph1 = nullptr, *ph2 = nullptr, *pz = nullptr;
+  std::vector<void*> owned;
+};
+
+namespace bmi {
+
+static int dalloc(bmi_ddpg* h, float** p, size_t n) {
+  void* q = nullptr;
+  BMI_CUDA_CHECK(cudaMalloc(&q, n * sizeof(float)));
+  BMI_CUDA_CHECK(cudaMemset(q, 0, n * sizeof(float)));
+  h->owned.push_back(q);
+  *p = (float*)q;
+  return BMI_OK;
+}
+
+// C[M][N] (row-major, ldc) = op(A)[M][K] * op(B)[K][N]  (+ bias[N], ReLU)
+static int gemm_rm(bmi_ddpg* h, cudaStream_t st, int opA, int opB, int M, int N, int K,
+                   const float* A, int lda, const float* B, int ldb, float* C, int ldc, int epi,
+                   const float* bias) {
+  GemmKey key{opA, opB, M, N, K, lda, ldb, ldc, epi, ptr_align(A), ptr_align(B), ptr_align(C)};
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    GemmPlan p;
+    BMI_CUBLAS_CHECK(cublasLtMatmulDescCreate(&p.desc, CUBLAS_COMPUTE_32F, CUDA_R_32F));
+    // column-major call: m = N, n = M, first operand = B, second = A
+    cublasOperation_t ta = opB ? CUBLAS_OP_T : CUBLAS_OP_N;
+    cublasOperation_t tb = opA ? CUBLAS_OP_T : CUBLAS_OP_N;
+    BMI_CUBLAS_CHECK(cublasLtMatmulDescSetAttribute(p.desc, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta)));
+    BMI_CUBLAS_CHECK(cublasLtMatmulDescSetAttribute(p.desc, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb)));
+    cublasLtEpilogue_t e = epi == EPI_RELU_BIAS ? CUBLASLT_EPILOGUE_RELU_BIAS
+                           : epi == EPI_BIAS    ? CUBLASLT_EPILOGUE_BIAS
+                                                : CUBLASLT_EPILOGUE_DEFAULT;
+    BMI_CUBLAS_CHECK(cublasLtMatmulDescSetAttribute(p.desc, CUBLASLT_MATMUL_DESC_EPILOGUE, &e, sizeof(e)));
+    // stored (pre-op) shapes, column-major view of the row-major arrays
+    // first operand (row-major B): opB==N -> stored [K][N] row-major == col-major N x K
+    BMI_CUBLAS_CHECK(cublasLtMatrixLayoutCreate(&p.la, CUDA_R_32F, opB ? K : N, opB ? N : K, ldb));
+    BMI_CUBLAS_CHECK(cublasLtMatrixLayoutCreate(&p.lb, CUDA_R_32F, opA ? M : K, opA ? K : M, lda));
+    BMI_CUBLAS_CHECK(cublasLtMatrixLayoutCreate(&p.lc, CUDA_R_32F, N, M, ldc));
+    // the bias pointer is part of the descriptor, but only its presence matters for the
+    // heuristic; set a placeholder now and the real pointer on every call
+    if (epi != EPI_NONE) {
+      const void* bp = bias;
+      BMI_CUBLAS_CHECK(cublasLtMatmulDescSetAttribute(p.desc, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bp, sizeof(bp)));
+    }
+    cublasLtMatmulPreference_t pref;
+    BMI_CUBLAS_CHECK(cublasLtMatmulPreferenceCreate(&pref));
+    BMI_CUBLAS_CHECK(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES,
+                                                          &h->workspace_bytes, sizeof(h->workspace_bytes)));
+    // tell the heuristic how well the operands are really aligned (default assumes 256 B)
+    uint32_t al_first = (uint32_t)key.alB, al_second = (uint32_t)key.alA, al_c = (uint32_t)key.alC;
+    BMI_CUBLAS_CHECK(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_A_BYTES, &al_first, sizeof(al_first)));
+    BMI_CUBLAS_CHECK(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_B_BYTES, &al_second, sizeof(al_second)));
+    BMI_CUBLAS_CHECK(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_C_BYTES, &al_c, sizeof(al_c)));
+    BMI_CUBLAS_CHECK(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_D_BYTES, &al_c, sizeof(al_c)));
+    cublasLtMatmulHeuristicResult_t res;
+    int found = 0;
+    cublasStatus_t s = cublasLtMatmulAlgoGetHeuristic(h->lt, p.desc, p.la, p.lb, p.lc, p.lc, pref, 1, &res, &found);
+    cublasLtMatmulPreferenceDestroy(pref);
+    if (s != CUBLAS_STATUS_SUCCESS || found == 0) {
+      set_error("cublasLt heuristic found no algorithm for gemm opA=%d opB=%d M=%d N=%d K=%d epi=%d (status %d)",
+                opA, opB, M, N, K, epi, (int)s);
+      return BMI_ERR_CUBLAS;
+    }
+    p.algo = res.algo;
+    it = h->plans.emplace(key, p).first;
+  }
+  GemmPlan& p = it->second;
+  if (epi != EPI_NONE) {
+    const void* bp = bias;
+    BMI_CUBLAS_CHECK(cublasLtMatmulDescSetAttribute(p.desc, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bp, sizeof(bp)));
+  }
+  const float one = 1.0f, zero = 0.0f;
+  BMI_CUBLAS_CHECK(cublasLtMatmul(h->lt, p.desc, &one, B, p.la, A, p.lb, &zero, C, p.lc, C, p.lc, &p.algo,
+                                  h->workspace, h->workspace_bytes, st));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return BMI_OK;
+}
+
+// ---- elementwise / reduction kernels ------------------------------------------------------
+// xc[r] = [x[r], a[r] / amax]
+__global__ void concat_scale_kernel(const float* __restrict__ x, const float* __restrict__ a, int n,
+                                    int Dx, int Da, float amax, float* __restrict__ xc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int D = Dx + Da;
+  if (i >= n * D) return;
+  int r = i / D, j = i % D;
+  xc[i] = j < Dx ? x[r * Dx + j] : __fdiv_rn(a[r * Da + (j - Dx)], amax);
+}
+
+__global__ void tanh_scale_kernel(const float* __restrict__ z, int n, float amax,
+                                  float* __restrict__ a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = amax * tanhf(z[i]);
+}
+
+// y = clamp(r + gamma * q_next, -1/(1-gamma), 0)   (ddpg_agent.py:255-260)
+__global__ void target_kernel(const float* __restrict__ r, const float* __restrict__ qn, int n,
+                              float gamma, float clip_ret, float* __restrict__ y) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fminf(fmaxf(__fadd_rn(r[i], __fmul_rn(gamma, qn[i])), -clip_ret), 0.0f);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = l < (int)(blockDim.x >> 5) ? sm[l] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
+
+// critic loss = mean((y - q)^2); dq = 2 (q - y) / B          single block
+__global__ void critic_loss_kernel(const float* __restrict__ y, const float* __restrict__ q, int B,
+                                   float* __restrict__ dq, float* __restrict__ loss) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    float d = y[i] - q[i];
+    acc += d * d;
+    dq[i] = -2.0f * d / (float)B;
+  }
+  float t = block_sum(acc, sm);
+  if (threadIdx.x == 0) *loss = t / (float)B;
+}
+
+// actor loss = -mean(qa) + l2 * mean((a/amax)^2);  dqa = -1/B;
+// dz = (da_q/amax + 2 l2 a / (amax^2 B Da)) * amax (1 - tanh^2),  tanh = a/amax
+__global__ void actor_loss_kernel(const float* __restrict__ qa, const float* __restrict__ a,
+                                  const float* __restrict__ dxc, int B, int Dx, int Da, float amax,
+                                  float l2, float* __restrict__ dz, float* __restrict__ loss) {
+  __shared__ float sm[32];
+  float accq = 0.f, acca = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) accq += qa[i];
+  const int n = B * Da;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int r = i / Da, j = i % Da;
+    float th = a[i] / amax;
+    acca += th * th;
+    float da = dxc[r * (Dx + Da) + Dx + j] / amax + l2 * 2.0f * th / (amax * (float)n);
+    dz[i] = da * amax * (1.0f - th * th);
+  }
+  float tq = block_sum(accq, sm);
+  float ta = block_sum(acca, sm);
+  if (threadIdx.x == 0) *loss = -tq / (float)B + l2 * ta / (float)n;
+}
+
+__global__ void fill_kernel(float* p, int n, float v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// dZ = dH * (H > 0) in place, db[j] = sum_r dZ[r][j].  One block per 32 columns, 8 row-lanes.
+__global__ void drelu_bgrad_kernel(float* __restrict__ dH, const float* __restrict__ H, int rows,
+                                   int cols, float* __restrict__ db) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols) {
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      float g = H[(size_t)r * cols + c] > 0.f ? dH[(size_t)r * cols + c] : 0.f;
+      dH[(size_t)r * cols + c] = g;
+      acc += g;
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    db[c] = t;
+  }
+}
+
+// db[j] = sum_r dZ[r][j] (no mask) for the output layer
+__global__ void bgrad_kernel(const float* __restrict__ dZ, int rows, int cols, float* __restrict__ db) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = threadIdx.y; r < rows; r += 8) acc += dZ[(size_t)r * cols + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    db[c] = t;
+  }
+}
+
+__global__ void adam_prepare_kernel(int* step, float* scal, float lr_a, float lr_c, float b1, float b2) {
+  int t = ++(*step);
+  double bc1 = 1.0 - pow((double)b1, (double)t);
+  double bc2 = 1.0 - pow((double)b2, (double)t);
+  scal[0] = (float)((double)lr_a / bc1);
+  scal[1] = (float)((double)lr_c / bc1);
+  scal[2] = (float)sqrt(bc2);
+}
+
+// torch.optim.Adam (_single_tensor_adam) on the concatenated [actor | critic] buffers
+__global__ void adam_kernel(float* __restrict__ pa, float* __restrict__ pc, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v, int64_t na, int64_t na_pad,
+                            int64_t n, const float* __restrict__ scal, float b1, float b2, float eps) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (i >= na && i < na_pad)) return;
+  float gi = g[i];
+  float mi = m[i] + (gi - m[i]) * (1.0f - b1);          // exp_avg.lerp_(grad, 1-beta1)
+  float vi = v[i] * b2 + (1.0f - b2) * gi * gi;         // mul_(beta2).addcmul_(g, g, 1-beta2)
+  m[i] = mi;
+  v[i] = vi;
+  float denom = sqrtf(vi) / scal[2] + eps;
+  float step = i < na ? scal[0] : scal[1];
+  float* p = i < na ? pa + i : pc + (i - na_pad);
+  *p = *p - step * (mi / denom);
+}
+
+// target = (1 - polyak) * param + polyak * target, separately rounded like torch
+__global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, int64_t n,
+                              float c_src, float c_tgt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tgt[i] = __fadd_rn(__fmul_rn(c_src, src[i]), __fmul_rn(c_tgt, tgt[i]));
+}
+
+__global__ void select_actions_kernel(const float* __restrict__ pi, int64_t n, int Da, float amax,
+                                      float noise_eps, float random_eps, float late_clip,
+                                      uint64_t seed, const uint64_t* __restrict__ counter,
+                                      float* __restrict__ out) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint64_t c = *counter + (uint64_t)r;
+  // block 0: two Box-Muller pairs -> up to 4 gaussians; block 1: 4 uniforms; block 2: bernoulli
+  Philox4 pg = philox4x32_10(seed, 3 * c, kStreamExplore);
+  Philox4 pu = philox4x32_10(seed, 3 * c + 1, kStreamExplore);
+  Philox4 pb = philox4x32_10(seed, 3 * c + 2, kStreamExplore);
+  const bool take_random = u24(pb.v[0]) < random_eps;
+  for (int j = 0; j < Da; ++j) {
+    int pair = (j >> 1) & 1;
+    float u1 = 1.0f - u24(pg.v[2 * pair]);  // (0,1]
+    float u2 = u24(pg.v[2 * pair + 1]);
+    float rad = sqrtf(-2.0f * logf(u1));
+    float gz = (j & 1) ? rad * sinf(6.28318530717958647692f * u2) : rad * cosf(6.28318530717958647692f * u2);
+    float a = pi[r * Da + j] + noise_eps * amax * gz;
+    a = fminf(fmaxf(a, -amax), amax);
+    float ra = -amax + 2.0f * amax * u24(pu.v[j & 3]);
+    if (take_random) a = ra;  // a += 1 * (ra - a)
+    if (late_clip > 0.f) a = fminf(fmaxf(a, -late_clip), late_clip);
+    out[r * Da + j] = a;
+  }
+}
+
+__global__ void advance_counter_kernel2(uint64_t* counter, uint64_t by) { *counter += by; }
+
+// forward through the three hidden layers (+ optional output layer) of a net
+static int mlp_hidden(bmi_ddpg* h, cudaStream_t st, const NetLayout& L, const float* P, const float* x,
+                      int rows, float* o1, float* o2, float* o3) {
+  int rc;
+  const int H = L.hidden;
+  if ((rc = gemm_rm(h, st, 0, 1, rows, H, L.in_dim, x, L.in_dim, P + L.w[0], L.in_dim, o1, H, EPI_RELU_BIAS, P + L.b[0]))) return rc;
+  if ((rc = gemm_rm(h, st, 0, 1, rows, H, H, o1, H, P + L.w[1], H, o2, H, EPI_RELU_BIAS, P + L.b[1]))) return rc;
+  if ((rc = gemm_rm(h, st, 0, 1, rows, H, H, o2, H, P + L.w[2], H, o3, H, EPI_RELU_BIAS, P + L.b[2]))) return rc;
+  return BMI_OK;
+}
+
+static int mlp_out(bmi_ddpg* h, cudaStream_t st, const NetLayout& L, const float* P, const float* h3,
+                   int rows, float* z) {
+  return gemm_rm(h, st, 0, 1, rows, L.out_dim, L.hidden, h3, L.hidden, P + L.w[3], L.hidden, z,
+                 L.out_dim, EPI_BIAS, P + L.b[3]);
+}
+
+// backward through a 4-layer MLP.  dz: [rows][out] grad wrt output pre-activation (clobbered
+// scratch d1/d2 hold hidden grads).  If G != nullptr parameter grads are written at G + offsets.
+// If dx != nullptr the input gradient [rows][in] is written.
+static int mlp_backward(bmi_ddpg* h, cudaStream_t st, const NetLayout& L, const float* P, float* G,
+                        const float* x, const float* a1, const float* a2, const float* a3,
+                        const float* dz, int rows, float* dx) {
+  int rc;
+  const int H = L.hidden, O = L.out_dim, I = L.in_dim;
+  dim3 blk(32, 8);
+  if (G) {
+    // dW4[O][H] = dz^T a3 ; db4 = colsum(dz)
+    if ((rc = gemm_rm(h, st, 1, 0, O, H, rows, dz, O, a3, H, G + L.w[3], H, EPI_NONE, nullptr))) return rc;
+    bgrad_kernel<<<(O + 31) / 32, blk, 0, st>>>(dz, rows, O, G + L.b[3]);
+    BMI_LAUNCHED();
+  }
+  // d3 = (dz W4) * relu'(a3)
+  if ((rc = gemm_rm(h, st, 0, 0, rows, H, O, dz, O, P + L.w[3], H, h->d1, H, EPI_NONE, nullptr))) return rc;
+  float* dump = h->dz;  // bias grads are a by-product of the mask kernel; scratch when unused
+  drelu_bgrad_kernel<<<(H + 31) / 32, blk, 0, st>>>(h->d1, a3, rows, H, G ? G + L.b[2] : dump);
+  BMI_LAUNCHED();
+  if (G)
+    if ((rc = gemm_rm(h, st, 1, 0, H, H, rows, h->d1, H, a2, H, G + L.w[2], H, EPI_NONE, nullptr))) return rc;
+  // d2 = (d3 W3) * relu'(a2)
+  if ((rc = gemm_rm(h, st, 0, 0, rows, H, H, h->d1, H, P + L.w[2], H, h->d2, H, EPI_NONE, nullptr))) return rc;
+  drelu_bgrad_kernel<<<(H + 31) / 32, blk, 0, st>>>(h->d2, a2, rows, H, G ? G + L.b[1] : dump);
+  BMI_LAUNCHED();
+  if (G)
+    if ((rc = gemm_rm(h, st, 1, 0, H, H, rows, h->d2, H, a1, H, G + L.w[1], H, EPI_NONE, nullptr))) return rc;
+  // d1 = (d2 W2) * relu'(a1)
+  if ((rc = gemm_rm(h, st, 0, 0, rows, H, H, h->d2, H, P + L.w[1], H, h->d1, H, EPI_NONE, nullptr))) return rc;
+  drelu_bgrad_kernel<<<(H + 31) / 32, blk, 0, st>>>(h->d1, a1, rows, H, G ? G + L.b[0] : dump);
+  BMI_LAUNCHED();
+  if (G)
+    if ((rc = gemm_rm(h, st, 1, 0, H, I, rows, h->d1, H, x, I, G + L.w[0], I, EPI_NONE, nullptr))) return rc;
+  if (dx)
+    if ((rc = gemm_rm(h, st, 0, 0, rows, I, H, h->d1, H, P + L.w[0], I, dx, I, EPI_NONE, nullptr))) return rc;
+  return BMI_OK;
+}
+
+}  // namespace bmi
+
+extern "C" int64_t bmi_ddpg_actor_param_count(const bmi_ddpg_config* c) {
+  if (!c) return -1;
+  NetLayout L;
+  L.init(c->obs_dim + c->goal_dim, c->hidden, c->act_dim);
+  return L.count;
+}
+extern "C" int64_t bmi_ddpg_critic_param_count(const bmi_ddpg_config* c) {
+  if (!c) return -1;
+  NetLayout L;
+  L.init(c->obs_dim + c->goal_dim + c->act_dim, c->hidden, 1);
+  return L.count;
+}
+
+extern "C" int bmi_ddpg_create(bmi_ddpg** out, const bmi_ddpg_config* cfg, float* actor, float* critic,
+                               float* actor_t, float* critic_t) {
+  BMI_REQUIRE(out && cfg && actor && critic && actor_t && critic_t, "bmi_ddpg_create: null pointer");
+  BMI_REQUIRE(cfg->obs_dim > 0 && cfg->goal_dim > 0 && cfg->act_dim > 0 && cfg->hidden > 0 &&
+                  cfg->batch > 0 && cfg->max_act_rows > 0,
+              "bmi_ddpg_create: bad dims");
+  BMI_REQUIRE(cfg->gamma >= 0.f && cfg->gamma < 1.f && cfg->clip_return > 0.f,
+              "bmi_ddpg_create: gamma must be in [0,1) and clip_return > 0");
+  bmi_ddpg* h = new bmi_ddpg();
+  h->cfg = *cfg;
+  const int Dx = cfg->obs_dim + cfg->goal_dim, Da = cfg->act_dim, H = cfg->hidden, B = cfg->batch;
+  h->la.init(Dx, H, Da);
+  h->lc.init(Dx + Da, H, 1);
+  h->actor = actor; h->critic = critic; h->actor_t = actor_t; h->critic_t = critic_t;
+  cublasStatus_t cs = cublasLtCreate(&h->lt);
+  if (cs != CUBLAS_STATUS_SUCCESS) {
+    set_error("cublasLtCreate failed with status %d", (int)cs);
+    delete h;
+    return BMI_ERR_CUBLAS;
+  }
+  int rc = 0;
+  h->na_pad = (h->la.count + 63) / 64 * 64;
+  h->n_grads = h->na_pad + h->lc.count;
+  const int64_t np = h->n_grads;
+#define A_(p, n) if (!rc) rc = dalloc(h, &h->p, (size_t)(n))
+  A_(grads, np); A_(adam_m, np); A_(adam_v, np); A_(adam_scal, 4);
+  A_(xc, B * (Dx + Da)); A_(h1, B * H); A_(h2, B * H); A_(h3, B * H);
+  A_(ch1, B * H); A_(ch2, B * H); A_(ch3, B * H); A_(q, B);
+  A_(ah1, B * H); A_(ah2, B * H); A_(ah3, B * H); A_(az, B * Da); A_(aa, B * Da);
+  A_(qh1, B * H); A_(qh2, B * H); A_(qh3, B * H); A_(qa, B); A_(xca, B * (Dx + Da));
+  A_(a_next, B * Da); A_(q_next, B); A_(y, B);
+  A_(d1, B * H); A_(d2, B * H); A_(dq, B > H ? B : H); A_(dxc, B * (Dx + Da)); A_(dz, B * Da > H ? B * Da : H);
+  A_(ph1, (size_t)cfg->max_act_rows * H); A_(ph2, (size_t)cfg->max_act_rows * H);
+  A_(pz, (size_t)cfg->max_act_rows * Da);
+#undef A_
+  if (!rc) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, sizeof(int)) != cudaSuccess || cudaMemset(p, 0, sizeof(int)) != cudaSuccess) {
+      set_error("bmi_ddpg_create: cudaMalloc(step) failed");
+      rc = BMI_ERR_CUDA;
+    } else {
+      h->owned.push_back(p);
+      h->adam_step = (int*)p;
+    }
+  }
+  if (!rc) {
+    if (cudaMalloc(&h->workspace, h->workspace_bytes) != cudaSuccess) {
+      set_error("bmi_ddpg_create: cudaMalloc(workspace) failed");
+      rc = BMI_ERR_CUDA;
+    }
+  }
+  if (rc) {
+    bmi_ddpg_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_destroy(bmi_ddpg* h) {
+  if (!h) return BMI_OK;
+  for (auto& kv : h->plans) {
+    cublasLtMatmulDescDestroy(kv.second.desc);
+    cublasLtMatrixLayoutDestroy(kv.second.la);
+    cublasLtMatrixLayoutDestroy(kv.second.lb);
+    cublasLtMatrixLayoutDestroy(kv.second.lc);
+  }
+  for (void* p : h->owned) cudaFree(p);
+  if (h->workspace) cudaFree(h->workspace);
+  if (h->lt) cublasLtDestroy(h->lt);
+  delete h;
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_act(bmi_ddpg* h, const float* x, int64_t n, int32_t use_target, float* actions,
+                            bmi_stream_t stream) {
+  BMI_REQUIRE(h && x && actions, "bmi_ddpg_act: null pointer");
+  BMI_REQUIRE(n >= 0 && n <= h->cfg.max_act_rows, "bmi_ddpg_act: n=%lld exceeds max_act_rows=%d",
+              (long long)n, h->cfg.max_act_rows);
+  if (n == 0) return BMI_OK;
+  cudaStream_t st = as_stream(stream);
+  const float* P = use_target ? h->actor_t : h->actor;
+  const int H = h->cfg.hidden, Da = h->cfg.act_dim;
+  int rc;
+  // ping-pong two hidden buffers: ph1 -> ph2 -> ph1
+  const NetLayout& L = h->la;
+  if ((rc = gemm_rm(h, st, 0, 1, (int)n, H, L.in_dim, x, L.in_dim, P + L.w[0], L.in_dim, h->ph1, H, EPI_RELU_BIAS, P + L.b[0]))) return rc;
+  if ((rc = gemm_rm(h, st, 0, 1, (int)n, H, H, h->ph1, H, P + L.w[1], H, h->ph2, H, EPI_RELU_BIAS, P + L.b[1]))) return rc;
+  if ((rc = gemm_rm(h, st, 0, 1, (int)n, H, H, h->ph2, H, P + L.w[2], H, h->ph1, H, EPI_RELU_BIAS, P + L.b[2]))) return rc;
+  if ((rc = mlp_out(h, st, L, P, h->ph1, (int)n, h->pz))) return rc;
+  int tot = (int)n * Da;
+  tanh_scale_kernel<<<(tot + 255) / 256, 256, 0, st>>>(h->pz, tot, h->cfg.action_max, actions);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_backward(bmi_ddpg* h, const float* x, const float* xn, const float* actions,
+                                 const float* r, float* losses, bmi_stream_t stream) {
+  BMI_REQUIRE(h && x && xn && actions && r && losses, "bmi_ddpg_backward: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const bmi_ddpg_config& c = h->cfg;
+  const int B = c.batch, Dx = c.obs_dim + c.goal_dim, Da = c.act_dim, Dc = Dx + Da;
+  const float amax = c.action_max;
+  float* Ga = h->grads;
+  float* Gc = h->grads + h->na_pad;
+  int rc;
+  // ---- target: y = clamp(r + gamma * Q'(x', pi'(x')), -1/(1-gamma), 0) -------------------
+  if ((rc = mlp_hidden(h, st, h->la, h->actor_t, xn, B, h->h1, h->h2, h->h3))) return rc;
+  if ((rc = mlp_out(h, st, h->la, h->actor_t, h->h3, B, h->az))) return rc;
+  tanh_scale_kernel<<<(B * Da + 255) / 256, 256, 0, st>>>(h->az, B * Da, amax, h->a_next);
+  BMI_LAUNCHED();
+  concat_scale_kernel<<<(B * Dc + 255) / 256, 256, 0, st>>>(xn, h->a_next, B, Dx, Da, amax, h->xc);
+  BMI_LAUNCHED();
+  if ((rc = mlp_hidden(h, st, h->lc, h->critic_t, h->xc, B, h->h1, h->h2, h->h3))) return rc;
+  if ((rc = mlp_out(h, st, h->lc, h->critic_t, h->h3, B, h->q_next))) return rc;
+  target_kernel<<<(B + 255) / 256, 256, 0, st>>>(r, h->q_next, B, c.gamma, c.clip_return, h->y);
+  BMI_LAUNCHED();
+  // ---- critic loss + backward -----------------------------------------------------------
+  concat_scale_kernel<<<(B * Dc + 255) / 256, 256, 0, st>>>(x, actions, B, Dx, Da, amax, h->xc);
+  BMI_LAUNCHED();
+  if ((rc = mlp_hidden(h, st, h->lc, h->critic, h->xc, B, h->ch1, h->ch2, h->ch3))) return rc;
+  if ((rc = mlp_out(h, st, h->lc, h->critic, h->ch3, B, h->q))) return rc;
+  critic_loss_kernel<<<1, 256, 0, st>>>(h->y, h->q, B, h->dq, losses + 1);
+  BMI_LAUNCHED();
+  if ((rc = mlp_backward(h, st, h->lc, h->critic, Gc, h->xc, h->ch1, h->ch2, h->ch3, h->dq, B, nullptr))) return rc;
+  // ---- actor loss + backward ------------------------------------------------------------
+  if ((rc = mlp_hidden(h, st, h->la, h->actor, x, B, h->ah1, h->ah2, h->ah3))) return rc;
+  if ((rc = mlp_out(h, st, h->la, h->actor, h->ah3, B, h->az))) return rc;
+  tanh_scale_kernel<<<(B * Da + 255) / 256, 256, 0, st>>>(h->az, B * Da, amax, h->aa);
+  BMI_LAUNCHED();
+  concat_scale_kernel<<<(B * Dc + 255) / 256, 256, 0, st>>>(x, h->aa, B, Dx, Da, amax, h->xca);
+  BMI_LAUNCHED();
+  if ((rc = mlp_hidden(h, st, h->lc, h->critic, h->xca, B, h->qh1, h->qh2, h->qh3))) return rc;
+  if ((rc = mlp_out(h, st, h->lc, h->critic, h->qh3, B, h->qa))) return rc;
+  fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(h->dq, B, -1.0f / (float)B);
+  BMI_LAUNCHED();
+  if ((rc = mlp_backward(h, st, h->lc, h->critic, nullptr, h->xca, h->qh1, h->qh2, h->qh3, h->dq, B, h->dxc))) return rc;
+  actor_loss_kernel<<<1, 256, 0, st>>>(h->qa, h->aa, h->dxc, B, Dx, Da, amax, c.action_l2, h->dz, losses);
+  BMI_LAUNCHED();
+  // dz now holds the gradient wrt the actor's output pre-activation; mlp_backward with G
+  // only uses d1/d2 as scratch so dz stays intact while it is consumed
+  if ((rc = mlp_backward(h, st, h->la, h->actor, Ga, x, h->ah1, h->ah2, h->ah3, h->dz, B, nullptr))) return rc;
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_grad_buffer(bmi_ddpg* h, float** grads, int64_t* n) {
+  BMI_REQUIRE(h && grads && n, "bmi_ddpg_grad_buffer: null pointer");
+  *grads = h->grads;
+  *n = h->n_grads;
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_adam_step(bmi_ddpg* h, bmi_stream_t stream) {
+  BMI_REQUIRE(h, "bmi_ddpg_adam_step: null handle");
+  cudaStream_t st = as_stream(stream);
+  const bmi_ddpg_config& c = h->cfg;
+  adam_prepare_kernel<<<1, 1, 0, st>>>(h->adam_step, h->adam_scal, c.lr_actor, c.lr_critic, c.adam_beta1, c.adam_beta2);
+  BMI_LAUNCHED();
+  const int64_t n = h->n_grads;
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->actor, h->critic, h->grads, h->adam_m, h->adam_v,
+                                                            h->la.count, h->na_pad, n, h->adam_scal, c.adam_beta1,
+                                                            c.adam_beta2, c.adam_eps);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_soft_update(bmi_ddpg* h, bmi_stream_t stream) {
+  BMI_REQUIRE(h, "bmi_ddpg_soft_update: null handle");
+  cudaStream_t st = as_stream(stream);
+  // (1 - polyak) is evaluated in double by python, then rounded to f32 when it meets the tensor
+  const float c_src = (float)(1.0 - (double)h->cfg.polyak), c_tgt = h->cfg.polyak;
+  polyak_kernel<<<(unsigned)((h->la.count + 255) / 256), 256, 0, st>>>(h->actor_t, h->actor, h->la.count, c_src, c_tgt);
+  BMI_LAUNCHED();
+  polyak_kernel<<<(unsigned)((h->lc.count + 255) / 256), 256, 0, st>>>(h->critic_t, h->critic, h->lc.count, c_src, c_tgt);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_select_actions(const float* pi, int64_t n, int32_t Da, float amax, float noise_eps,
+                                  float random_eps, float late_clip, uint64_t seed, uint64_t* counter,
+                                  float* out, bmi_stream_t stream) {
+  BMI_REQUIRE(n >= 0 && Da > 0 && Da <= 4, "bmi_select_actions: act_dim must be in [1,4]");
+  if (n == 0) return BMI_OK;
+  BMI_REQUIRE(pi && counter && out, "bmi_select_actions: null pointer");
+  cudaStream_t st = as_stream(stream);
+  select_actions_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pi, n, Da, amax, noise_eps, random_eps,
+                                                                     late_clip, seed, counter, out);
+  BMI_LAUNCHED();
+  advance_counter_kernel2<<<1, 1, 0, st>>>(counter, (uint64_t)n);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}

@@ -1,0 +1,361 @@
+// Episode store, sparse reward and HER "future" relabelling kernels.
+//
+// Reference behaviour restated here (paths relative to the reference tree):
+//   replay_buffer.py:32-43   store_episode        -> store_kernel
+//   bmirobot_env_push_F.py:20-23,84-90  reward    -> reward_kernel / inside her kernels
+//   her.py:13-41             sample_her_transitions -> her_gather_kernel / her_inputs_kernel
+//   ddpg_agent.py:229-248    clip + normalise + concat + f32 cast -> her_inputs_kernel
+//
+// Bit-exactness: every float64 operation that numpy performs is issued with the
+// round-to-nearest intrinsics (__dadd_rn/__dmul_rn/...) so nvcc cannot contract them
+// into FMAs; numpy's reduction order for a 3-vector norm is ((s0+s1)+s2) (verified
+// empirically, see tests/test_her_oracle.py).
+#include "common.cuh"
+
+namespace bmi {
+
+template <typename T>
+__device__ __forceinline__ double ld_as_f64(const T* p) {
+  return (double)(*p);
+}
+
+// ---- store ---------------------------------------------------------------------------
+template <typename TD, typename TS>
+__global__ void store_kernel(TD* __restrict__ dst, const TS* __restrict__ src,
+                             const int64_t* __restrict__ slots, int64_t row_elems) {
+  const int64_t e = blockIdx.x;
+  const int64_t slot = slots[e];
+  if (slot < 0) return;  // superseded duplicate (numpy fancy assignment: the last write wins)
+  const TS* s = src + e * row_elems;
+  TD* d = dst + slot * row_elems;
+  for (int64_t i = blockIdx.y * blockDim.x + threadIdx.x; i < row_elems;
+       i += (int64_t)gridDim.y * blockDim.x)
+    d[i] = (TD)s[i];
+}
+
+template <typename TD, typename TS>
+static int store_key(void* dst, const void* src, const int64_t* slots, int64_t n_ep,
+                     int64_t row_elems, cudaStream_t st) {
+  if (n_ep == 0) return BMI_OK;
+  int gy = (int)((row_elems + 255) / 256);
+  if (gy > 16) gy = 16;
+  dim3 grid((unsigned)n_ep, gy);
+  store_kernel<TD, TS><<<grid, 256, 0, st>>>((TD*)dst, (const TS*)src, slots, row_elems);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+// ---- reward --------------------------------------------------------------------------
+template <typename T>
+__global__ void reward_kernel(const T* __restrict__ ag, const T* __restrict__ g, int64_t n,
+                              int gd, double thr, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < gd; ++k) {
+    double d = __dsub_rn((double)ag[i * gd + k], (double)g[i * gd + k]);
+    double sq = __dmul_rn(d, d);
+    s = (k == 0) ? sq : __dadd_rn(s, sq);
+  }
+  double dist = __dsqrt_rn(s);
+  out[i] = (dist > thr) ? -1.0f : -0.0f;  // -(bool).astype(f32): False -> -0.0
+}
+
+// ---- HER gather ------------------------------------------------------------------------
+struct HerRow {
+  int64_t ep, t, ft;
+  bool her;
+};
+
+__device__ __forceinline__ HerRow her_row(const int64_t* ep_idx, const int64_t* t_idx,
+                                          const double* u_her, const double* u_off, int64_t b,
+                                          int T, double future_p) {
+  HerRow r;
+  r.ep = ep_idx[b];
+  r.t = t_idx[b];
+  r.her = u_her[b] < future_p;                                   // her.py:28
+  double off = __dmul_rn(u_off[b], (double)((int64_t)T - r.t));  // her.py:30
+  r.ft = r.t + 1 + (int64_t)off;                                 // her.py:31-32 (trunc)
+  return r;
+}
+
+// distance of two goal vectors held one component per lane (lanes [0,gd)), numpy order
+__device__ __forceinline__ double warp_goal_dist(double a, double g, int gd, int lane) {
+  double d = __dsub_rn(a, g);
+  double sq = __dmul_rn(d, d);
+  double s = __shfl_sync(0xffffffffu, sq, 0);
+  for (int k = 1; k < gd; ++k) s = __dadd_rn(s, __shfl_sync(0xffffffffu, sq, k));
+  return __dsqrt_rn(s);
+}
+
+// one warp per sampled transition
+template <typename T>
+__global__ void her_gather_kernel(bmi_episodes buf, const int64_t* __restrict__ ep_idx,
+                                  const int64_t* __restrict__ t_idx,
+                                  const double* __restrict__ u_her,
+                                  const double* __restrict__ u_off, int64_t B, double future_p,
+                                  double thr, bmi_transitions out) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int Tn = buf.T, Do = buf.obs_dim, Dg = buf.goal_dim, Da = buf.act_dim;
+  const HerRow r = her_row(ep_idx, t_idx, u_her, u_off, b, Tn, future_p);
+  const T* obs = (const T*)buf.obs + (r.ep * (Tn + 1) + r.t) * Do;  // row t, row t+1 follows
+  const T* ag = (const T*)buf.ag + (r.ep * (Tn + 1) + r.t) * Dg;
+  const T* gsrc = r.her ? (const T*)buf.ag + (r.ep * (Tn + 1) + r.ft) * Dg
+                        : (const T*)buf.g + (r.ep * Tn + r.t) * Dg;
+  const T* act = (const T*)buf.actions + (r.ep * Tn + r.t) * Da;
+  for (int i = lane; i < Do; i += 32) {
+    T o = obs[i], on = obs[Do + i];
+    if (out.obs) ((T*)out.obs)[b * Do + i] = o;
+    if (out.obs_next) ((T*)out.obs_next)[b * Do + i] = on;
+  }
+  for (int i = lane; i < Da; i += 32)
+    if (out.actions) ((T*)out.actions)[b * Da + i] = act[i];
+  T a0 = 0, a1 = 0, gv = 0;
+  if (lane < Dg) {
+    a0 = ag[lane];
+    a1 = ag[Dg + lane];
+    gv = gsrc[lane];
+    if (out.ag) ((T*)out.ag)[b * Dg + lane] = a0;
+    if (out.ag_next) ((T*)out.ag_next)[b * Dg + lane] = a1;
+    if (out.g) ((T*)out.g)[b * Dg + lane] = gv;
+  }
+  double dist = warp_goal_dist((double)a1, (double)gv, Dg, lane);
+  if (lane == 0 && out.r) out.r[b] = (dist > thr) ? -1.0f : -0.0f;
+}
+
+__device__ __forceinline__ double clipd(double v, double lim) {
+  // np.clip(v, -lim, lim) == minimum(maximum(v, -lim), lim)
+  return fmin(fmax(v, -lim), lim);
+}
+
+__device__ __forceinline__ float norm_clip_f32(double v, double clip_obs, float mean, float stdv,
+                                               double clip_range) {
+  double c = clipd(v, clip_obs);                                        // _preproc_og
+  double z = __ddiv_rn(__dsub_rn(c, (double)mean), (double)stdv);       // normalizer.normalize
+  return (float)clipd(z, clip_range);                                   // torch.tensor(f32)
+}
+
+template <typename T>
+__global__ void her_inputs_kernel(bmi_episodes buf, const int64_t* __restrict__ ep_idx,
+                                  const int64_t* __restrict__ t_idx,
+                                  const double* __restrict__ u_her,
+                                  const double* __restrict__ u_off, int64_t B, double future_p,
+                                  double thr, double clip_obs, double clip_range,
+                                  const float* __restrict__ o_mean, const float* __restrict__ o_std,
+                                  const float* __restrict__ g_mean, const float* __restrict__ g_std,
+                                  float* __restrict__ x, float* __restrict__ xn,
+                                  float* __restrict__ actions, float* __restrict__ rew) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int Tn = buf.T, Do = buf.obs_dim, Dg = buf.goal_dim, Da = buf.act_dim;
+  const int Dx = Do + Dg;
+  const HerRow r = her_row(ep_idx, t_idx, u_her, u_off, b, Tn, future_p);
+  const T* obs = (const T*)buf.obs + (r.ep * (Tn + 1) + r.t) * Do;
+  const T* ag = (const T*)buf.ag + (r.ep * (Tn + 1) + r.t) * Dg;
+  const T* gsrc = r.her ? (const T*)buf.ag + (r.ep * (Tn + 1) + r.ft) * Dg
+                        : (const T*)buf.g + (r.ep * Tn + r.t) * Dg;
+  const T* act = (const T*)buf.actions + (r.ep * Tn + r.t) * Da;
+  for (int i = lane; i < Do; i += 32) {
+    const float m = o_mean[i], s = o_std[i];
+    x[b * Dx + i] = norm_clip_f32((double)obs[i], clip_obs, m, s, clip_range);
+    xn[b * Dx + i] = norm_clip_f32((double)obs[Do + i], clip_obs, m, s, clip_range);
+  }
+  for (int i = lane; i < Da; i += 32) actions[b * Da + i] = (float)act[i];
+  T a1 = 0, gv = 0;
+  if (lane < Dg) {
+    a1 = ag[Dg + lane];
+    gv = gsrc[lane];
+    float gn = norm_clip_f32((double)gv, clip_obs, g_mean[lane], g_std[lane], clip_range);
+    x[b * Dx + Do + lane] = gn;
+    xn[b * Dx + Do + lane] = gn;  // g_next is the same relabelled goal (ddpg_agent.py:231)
+  }
+  double dist = warp_goal_dist((double)a1, (double)gv, Dg, lane);
+  if (lane == 0) rew[b] = (dist > thr) ? -1.0f : -0.0f;
+}
+
+// ---- device-side draws -------------------------------------------------------------------
+__global__ void her_draw_kernel(uint64_t seed, const uint64_t* __restrict__ counter, int64_t B,
+                                const int64_t* __restrict__ n_valid_p, int T,
+                                int64_t* __restrict__ ep_idx, int64_t* __restrict__ t_idx,
+                                double* __restrict__ u_her, double* __restrict__ u_off) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const uint64_t c = *counter + (uint64_t)b;
+  const int64_t n_valid = *n_valid_p;
+  Philox4 p0 = philox4x32_10(seed, 2 * c, kStreamHer);
+  Philox4 p1 = philox4x32_10(seed, 2 * c + 1, kStreamHer);
+  int64_t ep = (int64_t)__dmul_rn(u53(p0.v[0], p0.v[1]), (double)n_valid);
+  if (ep >= n_valid) ep = n_valid - 1;
+  ep_idx[b] = ep;
+  t_idx[b] = (int64_t)(((uint64_t)p0.v[2] * (uint64_t)T) >> 32);
+  u_her[b] = u53(p1.v[0], p1.v[1]);
+  u_off[b] = u53(p1.v[2], p1.v[3]);
+}
+
+__global__ void advance_counter_kernel(uint64_t* counter, uint64_t by) { *counter += by; }
+
+// ---- rollout record ----------------------------------------------------------------------
+template <typename T>
+__global__ void rollout_record_kernel(bmi_episodes ep, int t, const float* __restrict__ obs,
+                                      const float* __restrict__ ag, const float* __restrict__ g,
+                                      const float* __restrict__ act) {
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= ep.n_episodes) return;
+  const int Tn = ep.T, Do = ep.obs_dim, Dg = ep.goal_dim, Da = ep.act_dim;
+  T* o = (T*)ep.obs + (e * (Tn + 1) + t) * Do;
+  for (int i = lane; i < Do; i += 32) o[i] = (T)obs[e * Do + i];
+  if (lane < Dg) ((T*)ep.ag)[(e * (Tn + 1) + t) * Dg + lane] = (T)ag[e * Dg + lane];
+  if (t < Tn && g != nullptr && act != nullptr) {
+    if (lane < Dg) ((T*)ep.g)[(e * Tn + t) * Dg + lane] = (T)g[e * Dg + lane];
+    if (lane < Da) ((T*)ep.actions)[(e * Tn + t) * Da + lane] = (T)act[e * Da + lane];
+  }
+}
+
+static int check_eps(const bmi_episodes* b, const char* what) {
+  BMI_REQUIRE(b != nullptr, "%s: null episodes", what);
+  BMI_REQUIRE(b->dtype == BMI_F32 || b->dtype == BMI_F64, "%s: bad dtype %d", what, b->dtype);
+  BMI_REQUIRE(b->T > 0 && b->obs_dim > 0 && b->goal_dim > 0 && b->goal_dim <= 32 &&
+                  b->act_dim > 0 && b->act_dim <= 32,
+              "%s: bad dims T=%d obs=%d goal=%d act=%d", what, b->T, b->obs_dim, b->goal_dim,
+              b->act_dim);
+  return BMI_OK;
+}
+
+}  // namespace bmi
+
+using namespace bmi;
+
+extern "C" int bmi_buffer_store(const bmi_episodes* dst, const bmi_episodes* src,
+                                const int64_t* slots, bmi_stream_t stream) {
+  int rc;
+  if ((rc = check_eps(dst, "bmi_buffer_store(dst)"))) return rc;
+  if ((rc = check_eps(src, "bmi_buffer_store(src)"))) return rc;
+  BMI_REQUIRE(dst->T == src->T && dst->obs_dim == src->obs_dim && dst->goal_dim == src->goal_dim &&
+                  dst->act_dim == src->act_dim,
+              "bmi_buffer_store: src/dst dims differ");
+  BMI_REQUIRE(slots != nullptr || src->n_episodes == 0, "bmi_buffer_store: null slots");
+  cudaStream_t st = as_stream(stream);
+  const int64_t n = src->n_episodes;
+  const int64_t T = src->T;
+  const int64_t rows[4] = {(T + 1) * src->obs_dim, (T + 1) * src->goal_dim, T * src->goal_dim,
+                           T * src->act_dim};
+  void* d[4] = {dst->obs, dst->ag, dst->g, dst->actions};
+  const void* s[4] = {src->obs, src->ag, src->g, src->actions};
+  for (int k = 0; k < 4; ++k) {
+    if (dst->dtype == BMI_F64 && src->dtype == BMI_F64)
+      rc = store_key<double, double>(d[k], s[k], slots, n, rows[k], st);
+    else if (dst->dtype == BMI_F64)
+      rc = store_key<double, float>(d[k], s[k], slots, n, rows[k], st);
+    else if (src->dtype == BMI_F64)
+      rc = store_key<float, double>(d[k], s[k], slots, n, rows[k], st);
+    else
+      rc = store_key<float, float>(d[k], s[k], slots, n, rows[k], st);
+    if (rc) return rc;
+  }
+  return BMI_OK;
+}
+
+extern "C" int bmi_compute_reward(const void* ag, const void* g, int64_t n, int32_t goal_dim,
+                                  int32_t dtype, double thr, float* out, bmi_stream_t stream) {
+  BMI_REQUIRE(n >= 0 && goal_dim > 0, "bmi_compute_reward: bad sizes n=%lld gd=%d", (long long)n,
+              goal_dim);
+  BMI_REQUIRE(dtype == BMI_F32 || dtype == BMI_F64, "bmi_compute_reward: bad dtype %d", dtype);
+  if (n == 0) return BMI_OK;
+  BMI_REQUIRE(ag && g && out, "bmi_compute_reward: null pointer");
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == BMI_F64)
+    reward_kernel<double><<<grid, 256, 0, as_stream(stream)>>>((const double*)ag, (const double*)g,
+                                                               n, goal_dim, thr, out);
+  else
+    reward_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)ag, (const float*)g, n,
+                                                              goal_dim, thr, out);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_her_sample(const bmi_episodes* buf, int64_t n_valid, const int64_t* ep_idx,
+                              const int64_t* t_idx, const double* u_her, const double* u_off,
+                              int64_t B, double future_p, double thr, const bmi_transitions* out,
+                              bmi_stream_t stream) {
+  int rc;
+  if ((rc = check_eps(buf, "bmi_her_sample"))) return rc;
+  BMI_REQUIRE(B >= 0, "bmi_her_sample: negative batch");
+  if (B == 0) return BMI_OK;
+  BMI_REQUIRE(n_valid > 0 && n_valid <= buf->n_episodes,
+              "bmi_her_sample: n_valid=%lld outside (0, %lld] (sampling an empty buffer)",
+              (long long)n_valid, (long long)buf->n_episodes);
+  BMI_REQUIRE(ep_idx && t_idx && u_her && u_off && out, "bmi_her_sample: null pointer");
+  unsigned grid = (unsigned)((B + 3) / 4);
+  if (buf->dtype == BMI_F64)
+    her_gather_kernel<double><<<grid, 128, 0, as_stream(stream)>>>(*buf, ep_idx, t_idx, u_her,
+                                                                   u_off, B, future_p, thr, *out);
+  else
+    her_gather_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(*buf, ep_idx, t_idx, u_her,
+                                                                  u_off, B, future_p, thr, *out);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_her_sample_inputs(const bmi_episodes* buf, int64_t n_valid,
+                                     const int64_t* ep_idx, const int64_t* t_idx,
+                                     const double* u_her, const double* u_off, int64_t B,
+                                     double future_p, double thr, double clip_obs,
+                                     double clip_range, const float* o_mean, const float* o_std,
+                                     const float* g_mean, const float* g_std, float* x, float* xn,
+                                     float* actions, float* r, bmi_stream_t stream) {
+  int rc;
+  if ((rc = check_eps(buf, "bmi_her_sample_inputs"))) return rc;
+  BMI_REQUIRE(B >= 0, "bmi_her_sample_inputs: negative batch");
+  if (B == 0) return BMI_OK;
+  BMI_REQUIRE(n_valid != 0, "bmi_her_sample_inputs: sampling an empty buffer");
+  BMI_REQUIRE(ep_idx && t_idx && u_her && u_off && o_mean && o_std && g_mean && g_std && x && xn &&
+                  actions && r,
+              "bmi_her_sample_inputs: null pointer");
+  unsigned grid = (unsigned)((B + 3) / 4);
+  if (buf->dtype == BMI_F64)
+    her_inputs_kernel<double><<<grid, 128, 0, as_stream(stream)>>>(
+        *buf, ep_idx, t_idx, u_her, u_off, B, future_p, thr, clip_obs, clip_range, o_mean, o_std,
+        g_mean, g_std, x, xn, actions, r);
+  else
+    her_inputs_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(
+        *buf, ep_idx, t_idx, u_her, u_off, B, future_p, thr, clip_obs, clip_range, o_mean, o_std,
+        g_mean, g_std, x, xn, actions, r);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_her_draw(uint64_t seed, uint64_t* counter, int64_t B, const int64_t* n_valid,
+                            int32_t T, int64_t* ep_idx, int64_t* t_idx, double* u_her,
+                            double* u_off, bmi_stream_t stream) {
+  BMI_REQUIRE(B >= 0 && T > 0, "bmi_her_draw: bad sizes");
+  if (B == 0) return BMI_OK;
+  BMI_REQUIRE(counter && n_valid && ep_idx && t_idx && u_her && u_off, "bmi_her_draw: null pointer");
+  her_draw_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(
+      seed, counter, B, n_valid, T, ep_idx, t_idx, u_her, u_off);
+  BMI_LAUNCHED();
+  advance_counter_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, (uint64_t)B);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_rollout_record(const bmi_episodes* ep, int32_t t, const float* obs,
+                                  const float* ag, const float* g, const float* act,
+                                  bmi_stream_t stream) {
+  int rc;
+  if ((rc = check_eps(ep, "bmi_rollout_record"))) return rc;
+  BMI_REQUIRE(t >= 0 && t <= ep->T, "bmi_rollout_record: t=%d outside [0,%d]", t, ep->T);
+  BMI_REQUIRE(obs && ag, "bmi_rollout_record: null obs/ag");
+  BMI_REQUIRE(t == ep->T || (g && act), "bmi_rollout_record: null g/actions for t<T");
+  if (ep->n_episodes == 0) return BMI_OK;
+  unsigned grid = (unsigned)((ep->n_episodes + 3) / 4);
+  if (ep->dtype == BMI_F64)
+    rollout_record_kernel<double><<<grid, 128, 0, as_stream(stream)>>>(*ep, t, obs, ag, g, act);
+  else
+    rollout_record_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(*ep, t, obs, ag, g, act);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
