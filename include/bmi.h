@@ -133,8 +133,10 @@ int bmi_her_draw(uint64_t seed, uint64_t* counter_dev, int64_t B, const int64_t*
  * normalizer (normalizer.py:5-70).  All accumulators are float32 device arrays owned by
  * the caller: local_sum[size], local_sumsq[size], local_count[1], total_*[...], mean, std.
  * ---------------------------------------------------------------------------------- */
-/* normalizer.update (normalizer.py:25-31): v is [n_rows][size] in dtype. */
-int bmi_norm_update(const void* v_dev, int64_t n_rows, int32_t size, int32_t dtype,
+/* normalizer.update (normalizer.py:25-31): v is [n_rows][size] in dtype.  pre_clip > 0 applies
+ * ddpg_agent._preproc_og's np.clip(v, -pre_clip, pre_clip) (ddpg_agent.py:214-217) to each element
+ * before it is accumulated; pass 0 (or inf) for no clipping. */
+int bmi_norm_update(const void* v_dev, int64_t n_rows, int32_t size, int32_t dtype, double pre_clip,
                     float* local_sum_dev, float* local_sumsq_dev, float* local_count_dev,
                     bmi_stream_t stream);
 /* normalizer.recompute_stats (normalizer.py:40-57).  The caller first SUMS local_* over

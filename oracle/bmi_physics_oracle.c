@@ -1,0 +1,790 @@
+/*
+ * bmi_physics_oracle.c — CPU (double precision) restatement of the bmirobot environment step.
+ * TEST INFRASTRUCTURE ONLY: linked by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs; the product never loads it.
+ *
+ * PARITY UNPINNED against PyBullet itself: the reference delegates the arithmetic of this path
+ * to PyBullet 3.1.7 (README.md:10; Bullet btMultiBodyDynamicsWorld + BussIK), which is neither
+ * in the reference tree nor installable here.  This file restates the published algorithm
+ * (Featherstone forward dynamics, velocity-level MLCP solved by projected Gauss-Seidel with
+ * Bullet's row set-up, DLS inverse kinematics) and is pinned only on what the reference's own
+ * recorded trajectories (bmirobot_1000_*_demo.npz) determine: reset pose, block drop/settle
+ * transient (contact ERP 0.08, slop 1e-5, matched to 1e-6) and sliding friction.  The arm's
+ * permanent self-contact needs Bullet's GJK/EPA manifolds and is NOT modelled, so
+ * the arm trajectory of episode 0 is reproduced only qualitatively (tests/test_oracle_physics.py
+ * records the measured gap).
+ *
+ * Reference call sites restated (paths relative to the reference tree):
+ *   bmirobot_env/bmirobot_env_push_F.py:92-108   step: clip, action[3]=0, IK+motors, 20 sub-steps
+ *   bmirobot_env/bmirobot_env_push_F.py:110-165  reset
+ *   bmirobot_env/bmirobot_env_push_F.py:169-237  27-float observation
+ *   bmirobot_env/bmirobot.py:129-191             applyAction / sent_hand_moving (motor set-points)
+ *   bmirobot_env/bmirobot_inverse_kinematics.py:28-33  position-only IK of link 11
+ *   bmirobot_env/bmirobot_env_pickandplace_v2.py:92-95 auto-grip rule (pick task)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/bmi_model.h"
+
+#define NL 9
+#define NU 15 /* generalized velocities: 9 joints + block linear 3 + block angular 3 */
+#define MAX_ROWS 192
+#define MAX_CONTACTS 48
+#define MAX_SHAPE_V 32
+#define MAX_SHAPE_P 64
+
+typedef struct {
+  int nl, ns;
+  int parent[NL], shape_of[NL];
+  double jpos[NL][3], jrot[NL][9], axis[NL][3], lo[NL], hi[NL], damp[NL], mass[NL], com[NL][3], inertia[NL][3], mu[NL];
+  int s_link[BMI_MAX_SHAPES], s_nv[BMI_MAX_SHAPES], s_np[BMI_MAX_SHAPES];
+  double s_v[BMI_MAX_SHAPES][MAX_SHAPE_V][3], s_p[BMI_MAX_SHAPES][MAX_SHAPE_P][4], s_c[BMI_MAX_SHAPES][3], s_r[BMI_MAX_SHAPES],
+      s_mu[BMI_MAX_SHAPES];
+  double P[BMI_MODEL_HDR];
+} Model;
+
+typedef struct {
+  double q[NL], qd[NL], qt[NL];
+  double bp[3], bq[4], bv[3], bw[3];
+  double goal[3];
+} State;
+
+typedef struct {
+  Model m;
+  int task;
+  double bh[3], bmass, binertia[3], bmu; /* block half extents / mass / diagonal inertia / friction */
+  /* statistics of the last step (for tests / tuning) */
+  int last_rows, last_iters, last_contacts;
+} Env;
+
+/* ------------------------------------------------------------------ small vector helpers */
+static void v3set(double* a, double x, double y, double z) { a[0] = x; a[1] = y; a[2] = z; }
+static void v3cpy(double* a, const double* b) { a[0] = b[0]; a[1] = b[1]; a[2] = b[2]; }
+static void v3add(double* o, const double* a, const double* b) { o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2]; }
+static void v3sub(double* o, const double* a, const double* b) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static double v3dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static void v3cross(double* o, const double* a, const double* b) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static void v3axpy(double* o, double s, const double* a) { o[0] += s * a[0]; o[1] += s * a[1]; o[2] += s * a[2]; }
+static double v3norm(const double* a) { return sqrt(v3dot(a, a)); }
+static void m3mul(double* o, const double* a, const double* b) { /* o = a b, row-major */
+  double t[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) t[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+  memcpy(o, t, sizeof(t));
+}
+static void m3vec(double* o, const double* a, const double* v) {
+  double x = a[0] * v[0] + a[1] * v[1] + a[2] * v[2], y = a[3] * v[0] + a[4] * v[1] + a[5] * v[2],
+         z = a[6] * v[0] + a[7] * v[1] + a[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static void m3tvec(double* o, const double* a, const double* v) { /* o = a^T v */
+  double x = a[0] * v[0] + a[3] * v[1] + a[6] * v[2], y = a[1] * v[0] + a[4] * v[1] + a[7] * v[2],
+         z = a[2] * v[0] + a[5] * v[1] + a[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+/* rotation about a unit axis (Rodrigues) */
+static void axis_angle(double* R, const double* u, double th) {
+  double c = cos(th), s = sin(th), C = 1 - c;
+  R[0] = c + u[0] * u[0] * C;        R[1] = u[0] * u[1] * C - u[2] * s; R[2] = u[0] * u[2] * C + u[1] * s;
+  R[3] = u[1] * u[0] * C + u[2] * s; R[4] = c + u[1] * u[1] * C;        R[5] = u[1] * u[2] * C - u[0] * s;
+  R[6] = u[2] * u[0] * C - u[1] * s; R[7] = u[2] * u[1] * C + u[0] * s; R[8] = c + u[2] * u[2] * C;
+}
+static void quat_to_mat(double* R, const double* q) { /* q = x,y,z,w */
+  double x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+/* roll, pitch, yaw of a rotation matrix (PyBullet getEulerFromQuaternion convention) */
+static void mat_to_euler(double* e, const double* R) {
+  double sarg = -R[6];
+  if (sarg <= -0.99999) { e[0] = 0; e[1] = -0.5 * M_PI; e[2] = atan2(-R[1], -R[2]); }   /* gimbal lock */
+  else if (sarg >= 0.99999) { e[0] = 0; e[1] = 0.5 * M_PI; e[2] = atan2(-R[1], R[2]); }
+  else { e[0] = atan2(R[7], R[8]); e[1] = asin(sarg); e[2] = atan2(R[3], R[0]); }
+}
+
+/* ------------------------------------------------------------------ model loading */
+static int load_model(Model* m, const float* b, int64_t n) {
+  if (n < BMI_MODEL_HDR || b[MP_MAGIC] != BMI_MODEL_MAGIC) return -1;
+  if ((int64_t)b[MP_TOTAL] != n) return -2;
+  memset(m, 0, sizeof(*m));
+  for (int i = 0; i < BMI_MODEL_HDR; ++i) m->P[i] = b[i];
+  m->nl = (int)b[MP_N_LINKS];
+  m->ns = (int)b[MP_N_SHAPES];
+  if (m->nl != NL || m->ns > BMI_MAX_SHAPES) return -3;
+  const float* lk = b + (int)b[MP_LINKS_OFF];
+  for (int i = 0; i < NL; ++i, lk += BMI_LINK_STRIDE) {
+    m->parent[i] = (int)lk[ML_PARENT];
+    for (int k = 0; k < 3; ++k) { m->jpos[i][k] = lk[ML_JPOS + k]; m->axis[i][k] = lk[ML_AXIS + k]; m->com[i][k] = lk[ML_COM + k]; m->inertia[i][k] = lk[ML_INERTIA + k]; }
+    for (int k = 0; k < 9; ++k) m->jrot[i][k] = lk[ML_JROT + k];
+    m->lo[i] = lk[ML_LO]; m->hi[i] = lk[ML_HI]; m->damp[i] = lk[ML_DAMPING]; m->mass[i] = lk[ML_MASS];
+    m->shape_of[i] = (int)lk[ML_SHAPE]; m->mu[i] = lk[ML_MU];
+  }
+  const float* sh = b + (int)b[MP_SHAPES_OFF];
+  const float* pool = b + (int)b[MP_POOL_OFF];
+  for (int s = 0; s < m->ns; ++s, sh += BMI_SHAPE_STRIDE) {
+    m->s_link[s] = (int)sh[MS_LINK]; m->s_nv[s] = (int)sh[MS_NVERTS]; m->s_np[s] = (int)sh[MS_NPLANES];
+    if (m->s_nv[s] > MAX_SHAPE_V || m->s_np[s] > MAX_SHAPE_P) return -4;
+    const float* v = pool + (int)sh[MS_VERT_OFF];
+    const float* p = pool + (int)sh[MS_PLANE_OFF];
+    for (int k = 0; k < m->s_nv[s]; ++k) v3set(m->s_v[s][k], v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+    for (int k = 0; k < m->s_np[s]; ++k) for (int c = 0; c < 4; ++c) m->s_p[s][k][c] = p[4 * k + c];
+    v3set(m->s_c[s], sh[MS_SPHERE_C], sh[MS_SPHERE_C + 1], sh[MS_SPHERE_C + 2]);
+    m->s_r[s] = sh[MS_SPHERE_R]; m->s_mu[s] = sh[MS_MU];
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ kinematics */
+typedef struct {
+  double R[NL][9], p[NL][3], z[NL][3], c[NL][3]; /* link rotation, origin, joint axis (world), COM */
+} Kin;
+
+static void fk(const Model* m, const double* q, Kin* k) {
+  for (int i = 0; i < NL; ++i) {
+    double Rq[9], Rl[9];
+    axis_angle(Rq, m->axis[i], q[i]);
+    m3mul(Rl, m->jrot[i], Rq); /* parent-from-child */
+    int pa = m->parent[i];
+    if (pa < 0) {
+      memcpy(k->R[i], Rl, sizeof(Rl));
+      v3set(k->p[i], m->P[MP_BASE_PX] + m->jpos[i][0], m->P[MP_BASE_PY] + m->jpos[i][1], m->P[MP_BASE_PZ] + m->jpos[i][2]);
+    } else {
+      m3mul(k->R[i], k->R[pa], Rl);
+      double t[3];
+      m3vec(t, k->R[pa], m->jpos[i]);
+      v3add(k->p[i], k->p[pa], t);
+    }
+    m3vec(k->z[i], k->R[i], m->axis[i]);
+    double t[3];
+    m3vec(t, k->R[i], m->com[i]);
+    v3add(k->c[i], k->p[i], t);
+  }
+}
+
+/* translational Jacobian (3 x 9, row-major) of world point x rigidly attached to link l */
+static void point_jacobian(const Model* m, const Kin* k, int l, const double* x, double* J) {
+  memset(J, 0, sizeof(double) * 27);
+  for (int j = l; j >= 0; j = m->parent[j]) {
+    double r[3], c[3];
+    v3sub(r, x, k->p[j]);
+    v3cross(c, k->z[j], r);
+    J[j] = c[0]; J[9 + j] = c[1]; J[18 + j] = c[2];
+  }
+}
+
+/* recursive Newton-Euler in world coordinates: tau = M(q) qdd + bias(q, qd) with gravity gz and
+ * Bullet's per-link velocity damping (force m v (k + k|v|), torque I w (k + k|w|) at the COM). */
+static void rnea(const Model* m, const Kin* k, const double* qd, const double* qdd, double gz, double kl, double ka,
+                 double* tau) {
+  double w[NL][3], al[NL][3], a[NL][3], vo[NL][3]; /* ang vel, ang acc, origin acc, origin vel */
+  double f[NL][3], n[NL][3];
+  for (int i = 0; i < NL; ++i) {
+    int pa = m->parent[i];
+    double wp[3] = {0, 0, 0}, alp[3] = {0, 0, 0}, ap[3] = {0, 0, -gz}, vp[3] = {0, 0, 0}, r[3] = {0, 0, 0};
+    if (pa >= 0) {
+      v3cpy(wp, w[pa]); v3cpy(alp, al[pa]); v3cpy(ap, a[pa]); v3cpy(vp, vo[pa]);
+      v3sub(r, k->p[i], k->p[pa]);
+    }
+    double t[3], t2[3];
+    /* origin velocity / acceleration of link i (its origin is rigidly attached to the parent) */
+    v3cross(t, wp, r); v3add(vo[i], vp, t);
+    v3cross(t, alp, r); v3add(a[i], ap, t);
+    v3cross(t, wp, r); v3cross(t2, wp, t); v3add(a[i], a[i], t2);
+    /* angular */
+    v3cpy(w[i], wp); v3axpy(w[i], qd[i], k->z[i]);
+    v3cpy(al[i], alp); v3axpy(al[i], qdd[i], k->z[i]);
+    v3cross(t, wp, k->z[i]); v3axpy(al[i], qd[i], t);
+    /* COM acceleration, force and moment */
+    double rc[3], ac[3], vc[3];
+    v3sub(rc, k->c[i], k->p[i]);
+    v3cross(t, al[i], rc); v3add(ac, a[i], t);
+    v3cross(t, w[i], rc); v3cross(t2, w[i], t); v3add(ac, ac, t2);
+    v3cross(t, w[i], rc); v3add(vc, vo[i], t);
+    double F[3], N[3], Iw[3], wl[3], all_[3], tl[3];
+    for (int c = 0; c < 3; ++c) F[c] = m->mass[i] * ac[c];
+    double vn = v3norm(vc);
+    v3axpy(F, m->mass[i] * (kl + kl * vn), vc);
+    /* I (world) x = R diag(I) R^T x */
+    m3tvec(wl, k->R[i], w[i]); m3tvec(all_, k->R[i], al[i]);
+    for (int c = 0; c < 3; ++c) tl[c] = m->inertia[i][c] * wl[c];
+    m3vec(Iw, k->R[i], tl);
+    for (int c = 0; c < 3; ++c) tl[c] = m->inertia[i][c] * all_[c];
+    m3vec(N, k->R[i], tl);
+    v3cross(t, w[i], Iw); v3add(N, N, t);
+    double wn = v3norm(w[i]);
+    v3axpy(N, (ka + ka * wn), Iw);
+    v3cpy(f[i], F);
+    v3cross(t, rc, F); v3add(n[i], N, t); /* moment about the link origin */
+  }
+  for (int i = NL - 1; i >= 0; --i) {
+    tau[i] = v3dot(k->z[i], n[i]);
+    int pa = m->parent[i];
+    if (pa >= 0) {
+      double r[3], t[3];
+      v3sub(r, k->p[i], k->p[pa]);
+      v3add(f[pa], f[pa], f[i]);
+      v3cross(t, r, f[i]);
+      v3add(n[pa], n[pa], n[i]);
+      v3add(n[pa], n[pa], t);
+    }
+  }
+}
+
+/* Cholesky of an n x n SPD matrix (row-major, ld NL), in place (lower); returns 0 on success */
+static int chol9(double* A) {
+  for (int j = 0; j < NL; ++j) {
+    double d = A[j * NL + j];
+    for (int k = 0; k < j; ++k) d -= A[j * NL + k] * A[j * NL + k];
+    if (d <= 0) return -1;
+    d = sqrt(d);
+    A[j * NL + j] = d;
+    for (int i = j + 1; i < NL; ++i) {
+      double s = A[i * NL + j];
+      for (int k = 0; k < j; ++k) s -= A[i * NL + k] * A[j * NL + k];
+      A[i * NL + j] = s / d;
+    }
+  }
+  return 0;
+}
+static void chol9_solve(const double* Lm, const double* b, double* x) {
+  double y[NL];
+  for (int i = 0; i < NL; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= Lm[i * NL + k] * y[k];
+    y[i] = s / Lm[i * NL + i];
+  }
+  for (int i = NL - 1; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < NL; ++k) s -= Lm[k * NL + i] * x[k];
+    x[i] = s / Lm[i * NL + i];
+  }
+}
+
+/* ------------------------------------------------------------------ inverse kinematics
+ * PyBullet calculateInverseKinematics without null-space arrays = BussIK damped least squares
+ * (IK2_VEL_DLS): up to ik_iters steps of dq = (J^T J + d I)^-1 J^T e from the current q, each
+ * step limited to ik_max_angle, stopping when |e| < ik_thresh.  Position only. */
+static void solve_sym9(double* A, double* b) { /* Gaussian elimination with partial pivoting, in place */
+  for (int c = 0; c < NL; ++c) {
+    int p = c;
+    for (int r = c + 1; r < NL; ++r) if (fabs(A[r * NL + c]) > fabs(A[p * NL + c])) p = r;
+    if (p != c) {
+      for (int k = 0; k < NL; ++k) { double t = A[c * NL + k]; A[c * NL + k] = A[p * NL + k]; A[p * NL + k] = t; }
+      double t = b[c]; b[c] = b[p]; b[p] = t;
+    }
+    double d = A[c * NL + c];
+    for (int r = c + 1; r < NL; ++r) {
+      double f = A[r * NL + c] / d;
+      for (int k = c; k < NL; ++k) A[r * NL + k] -= f * A[c * NL + k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = NL - 1; r >= 0; --r) {
+    double s = b[r];
+    for (int k = r + 1; k < NL; ++k) s -= A[r * NL + k] * b[k];
+    b[r] = s / A[r * NL + r];
+  }
+}
+
+static void ee_point(const Model* m, const Kin* k, double* x) {
+  int ee = (int)m->P[MP_EE_LINK];
+  v3cpy(x, k->p[ee]); /* link-frame origin, getLinkState(...)[4] (bmirobot.py:144-145) */
+}
+
+static void solve_ik(const Model* m, const double* q0, const double* target, double* qout) {
+  double q[NL];
+  memcpy(q, q0, sizeof(q));
+  int iters = (int)m->P[MP_IK_ITERS];
+  int ee = (int)m->P[MP_EE_LINK];
+  for (int it = 0; it < iters; ++it) {
+    Kin k;
+    fk(m, q, &k);
+    double x[3], e[3], J[27];
+    ee_point(m, &k, x);
+    v3sub(e, target, x);
+    if (v3norm(e) <= m->P[MP_IK_THRESH]) break;
+    point_jacobian(m, &k, ee, x, J);
+    double A[NL * NL], b[NL];
+    for (int i = 0; i < NL; ++i) {
+      for (int j = 0; j < NL; ++j) A[i * NL + j] = J[i] * J[j] + J[9 + i] * J[9 + j] + J[18 + i] * J[18 + j];
+      A[i * NL + i] += m->P[MP_IK_DAMPING];
+      b[i] = J[i] * e[0] + J[9 + i] * e[1] + J[18 + i] * e[2];
+    }
+    solve_sym9(A, b);
+    double mx = 0;
+    for (int i = 0; i < NL; ++i) if (fabs(b[i]) > mx) mx = fabs(b[i]);
+    double sc = mx > m->P[MP_IK_MAX_ANGLE] ? m->P[MP_IK_MAX_ANGLE] / mx : 1.0;
+    for (int i = 0; i < NL; ++i) q[i] += sc * b[i];
+  }
+  memcpy(qout, q, sizeof(q));
+}
+
+/* ------------------------------------------------------------------ constraint rows */
+typedef struct {
+  double J[NU], W[NU]; /* Jacobian row and M^-1 J^T */
+  double inv_diag, rhs, lo, hi, lambda;
+  int friction_of;     /* index of the normal row for friction rows, else -1 */
+  double mu;
+} Row;
+
+typedef struct {
+  int link;     /* arm link index or -1 (static world) */
+  int has_block;/* 1: body 1 is the block */
+  double x[3], n[3], dist, mu;
+} Contact;
+
+static void block_vertices(const Env* e, const State* s, const double* Rb, double v[8][3]) {
+  for (int k = 0; k < 8; ++k) {
+    double l[3] = {(k & 1 ? 1 : -1) * e->bh[0], (k & 2 ? 1 : -1) * e->bh[1], (k & 4 ? 1 : -1) * e->bh[2]}, t[3];
+    m3vec(t, Rb, l);
+    v3add(v[k], s->bp, t);
+  }
+}
+
+/* keep the `cap` candidates with the smallest distance (ties: lowest index), in index order */
+static int select_deepest(const double* dist, int n, double margin, int cap, int* out) {
+  int picked[64] = {0}, cnt = 0;
+  for (int r = 0; r < cap; ++r) {
+    int best = -1;
+    for (int i = 0; i < n; ++i)
+      if (!picked[i] && dist[i] < margin && (best < 0 || dist[i] < dist[best])) best = i;
+    if (best < 0) break;
+    picked[best] = 1;
+    ++cnt;
+  }
+  int o = 0;
+  for (int i = 0; i < n; ++i) if (picked[i]) out[o++] = i;
+  return cnt;
+}
+
+static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C) {
+  const Model* m = &e->m;
+  int nc = 0;
+  double Rb[9], bv[8][3];
+  quat_to_mat(Rb, s->bq);
+  block_vertices(e, s, Rb, bv);
+  const double tz = m->P[MP_TABLE_Z];
+  /* block vertices vs table plane: up to 4 deepest */
+  {
+    double d[8];
+    int sel[8];
+    for (int i = 0; i < 8; ++i) d[i] = bv[i][2] - tz;
+    int n = select_deepest(d, 8, m->P[MP_TABLE_MARGIN], 4, sel);
+    for (int i = 0; i < n; ++i) {
+      Contact* c = &C[nc++];
+      c->link = -1; c->has_block = 1; v3cpy(c->x, bv[sel[i]]); v3set(c->n, 0, 0, 1);
+      c->dist = d[sel[i]]; c->mu = e->bmu * m->P[MP_MU_TABLE];
+    }
+  }
+  double brad = v3norm(e->bh);
+  for (int sidx = 0; sidx < m->ns; ++sidx) {
+    int l = m->s_link[sidx], nv = m->s_nv[sidx], np = m->s_np[sidx];
+    double wv[MAX_SHAPE_V][3];
+    for (int i = 0; i < nv; ++i) { double t[3]; m3vec(t, k->R[l], m->s_v[sidx][i]); v3add(wv[i], k->p[l], t); }
+    /* hull vertices vs table plane: up to 2 deepest */
+    {
+      double d[MAX_SHAPE_V];
+      int sel[MAX_SHAPE_V];
+      for (int i = 0; i < nv; ++i) d[i] = wv[i][2] - tz;
+      int n = select_deepest(d, nv, m->P[MP_CONTACT_MARGIN], 2, sel);
+      for (int i = 0; i < n; ++i) {
+        Contact* c = &C[nc++];
+        c->link = l; c->has_block = 0; v3cpy(c->x, wv[sel[i]]); v3set(c->n, 0, 0, 1);
+        c->dist = d[sel[i]]; c->mu = m->s_mu[sidx] * m->P[MP_MU_TABLE];
+      }
+    }
+    /* block vs hull: broadphase on bounding spheres */
+    double cw[3], t[3], dd[3];
+    m3vec(t, k->R[l], m->s_c[sidx]); v3add(cw, k->p[l], t);
+    v3sub(dd, s->bp, cw);
+    if (v3norm(dd) > m->s_r[sidx] + brad + m->P[MP_BLOCK_MARGIN]) continue;
+    double d[8 + MAX_SHAPE_V], nrm[8 + MAX_SHAPE_V][3];
+    /* (a) block vertices against the hull planes: signed distance = max over planes */
+    for (int i = 0; i < 8; ++i) {
+      double xl[3], r[3];
+      v3sub(r, bv[i], k->p[l]); m3tvec(xl, k->R[l], r);
+      double best = -1e30; int bp = 0;
+      for (int p = 0; p < np; ++p) {
+        double sd = m->s_p[sidx][p][0] * xl[0] + m->s_p[sidx][p][1] * xl[1] + m->s_p[sidx][p][2] * xl[2] + m->s_p[sidx][p][3];
+        if (sd > best) { best = sd; bp = p; }
+      }
+      d[i] = best;
+      m3vec(nrm[i], k->R[l], m->s_p[sidx][bp]); /* outward hull normal: from link towards block */
+    }
+    /* (b) hull vertices against the block box: signed distance = max over the 6 faces */
+    for (int i = 0; i < nv; ++i) {
+      double xb[3], r[3];
+      v3sub(r, wv[i], s->bp); m3tvec(xb, Rb, r);
+      double best = -1e30; int ba = 0; double sg = 1;
+      for (int a = 0; a < 3; ++a) {
+        double sd = fabs(xb[a]) - e->bh[a];
+        if (sd > best) { best = sd; ba = a; sg = xb[a] >= 0 ? 1 : -1; }
+      }
+      d[8 + i] = best;
+      double ln[3] = {0, 0, 0}, wn[3];
+      ln[ba] = sg;
+      m3vec(wn, Rb, ln); /* outward block normal: from block towards link; flip -> from link to block */
+      v3set(nrm[8 + i], -wn[0], -wn[1], -wn[2]);
+    }
+    int sel[8 + MAX_SHAPE_V];
+    int n = select_deepest(d, 8 + nv, m->P[MP_BLOCK_MARGIN], 3, sel);
+    for (int i = 0; i < n; ++i) {
+      int ci = sel[i];
+      Contact* c = &C[nc++];
+      c->link = l; c->has_block = 1;
+      v3cpy(c->x, ci < 8 ? bv[ci] : wv[ci - 8]);
+      v3cpy(c->n, nrm[ci]); /* normal from the link (body 2) towards the block (body 1) */
+      c->dist = d[ci]; c->mu = e->bmu * m->s_mu[sidx];
+    }
+  }
+  return nc;
+}
+
+/* two unit tangents orthogonal to n (Bullet btPlaneSpace1) */
+static void plane_space(const double* n, double* p, double* q) {
+  if (fabs(n[2]) > 0.7071067811865475244) {
+    double a = n[1] * n[1] + n[2] * n[2], k = 1.0 / sqrt(a);
+    v3set(p, 0, -n[2] * k, n[1] * k);
+    v3set(q, a * k, -n[0] * p[2], n[0] * p[1]);
+  } else {
+    double a = n[0] * n[0] + n[1] * n[1], k = 1.0 / sqrt(a);
+    v3set(p, -n[1] * k, n[0] * k, 0);
+    v3set(q, -n[2] * p[1], n[2] * p[0], a * k);
+  }
+}
+
+/* fill J for direction dir at contact c (body 1 = block and/or body 2 = link; world static) */
+static void contact_jacobian(const Env* e, const State* s, const Kin* k, const Contact* c, const double* dir, double* J) {
+  memset(J, 0, sizeof(double) * NU);
+  if (c->has_block) {
+    double r[3], t[3];
+    v3sub(r, c->x, s->bp);
+    v3cross(t, r, dir);
+    for (int a = 0; a < 3; ++a) { J[9 + a] = dir[a]; J[12 + a] = t[a]; }
+  }
+  if (c->link >= 0) {
+    double Jp[27];
+    point_jacobian(&e->m, k, c->link, c->x, Jp);
+    double sgn = c->has_block ? -1.0 : 1.0; /* link is body 2 when the block is present */
+    for (int j = 0; j < NL; ++j) J[j] = sgn * (dir[0] * Jp[j] + dir[1] * Jp[9 + j] + dir[2] * Jp[18 + j]);
+  }
+}
+
+static void apply_minv(const Env* e, const double* Lm, const double* Ib_inv_world, const double* J, double* W) {
+  chol9_solve(Lm, J, W);
+  for (int a = 0; a < 3; ++a) W[9 + a] = J[9 + a] / e->bmass;
+  m3vec(W + 12, Ib_inv_world, J + 12);
+}
+
+static double dotn(const double* a, const double* b, int n) { double s = 0; for (int i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
+
+/* one simulation sub-step (Bullet btMultiBodyDynamicsWorld::stepSimulation restated) */
+static void substep(Env* e, State* s) {
+  const Model* m = &e->m;
+  const double dt = m->P[MP_DT], gz = m->P[MP_GRAVITY], kl = m->P[MP_LIN_DAMP], ka = m->P[MP_ANG_DAMP];
+  Kin k;
+  fk(m, s->q, &k);
+  /* mass matrix column by column and bias */
+  double M[NL * NL], bias[NL], zero[NL] = {0}, ej[NL];
+  rnea(m, &k, s->qd, zero, gz, kl, ka, bias);
+  for (int j = 0; j < NL; ++j) {
+    memset(ej, 0, sizeof(ej));
+    ej[j] = 1;
+    double col[NL];
+    rnea(m, &k, zero, ej, 0.0, 0.0, 0.0, col);
+    for (int i = 0; i < NL; ++i) M[i * NL + j] = col[i];
+  }
+  for (int i = 0; i < NL; ++i) for (int j = 0; j < i; ++j) M[i * NL + j] = M[j * NL + i] = 0.5 * (M[i * NL + j] + M[j * NL + i]);
+  double Lm[NL * NL];
+  memcpy(Lm, M, sizeof(M));
+  chol9(Lm);
+  /* unconstrained velocities */
+  double u[NU], tau[NL], acc[NL];
+  for (int i = 0; i < NL; ++i) tau[i] = -m->damp[i] * s->qd[i] - bias[i];
+  chol9_solve(Lm, tau, acc);
+  for (int i = 0; i < NL; ++i) u[i] = s->qd[i] + dt * acc[i];
+  double Rb[9];
+  quat_to_mat(Rb, s->bq);
+  {
+    double vn = v3norm(s->bv), wn = v3norm(s->bw);
+    for (int a = 0; a < 3; ++a) {
+      u[9 + a] = s->bv[a] + dt * (-(kl + kl * vn) * s->bv[a]);
+      u[12 + a] = s->bw[a] + dt * (-(ka + ka * wn) * s->bw[a]);
+    }
+    u[11] += dt * gz;
+  }
+  double Ibinv[9];
+  { /* R diag(1/I) R^T */
+    double t[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) t[3 * r + c] = Rb[3 * r + c] / e->binertia[c];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+      Ibinv[3 * r + c] = t[3 * r] * Rb[3 * c] + t[3 * r + 1] * Rb[3 * c + 1] + t[3 * r + 2] * Rb[3 * c + 2];
+  }
+  /* ---- rows ---- */
+  static Row rows[MAX_ROWS];
+  int nr = 0;
+  const double max_imp = m->P[MP_MOTOR_FORCE] * dt;
+  for (int j = 0; j < NL; ++j) { /* position motors: drive velocity to kp (q* - q)/dt + (1-kd) qd */
+    Row* r = &rows[nr++];
+    memset(r, 0, sizeof(*r));
+    r->J[j] = 1;
+    apply_minv(e, Lm, Ibinv, r->J, r->W);
+    r->inv_diag = 1.0 / r->W[j];
+    double target = m->P[MP_MOTOR_KP] * (s->qt[j] - s->q[j]) / dt + (1.0 - m->P[MP_MOTOR_KD]) * s->qd[j];
+    r->rhs = (target - u[j]) * r->inv_diag;
+    r->lo = -max_imp; r->hi = max_imp; r->friction_of = -1;
+  }
+  for (int j = 0; j < NL; ++j) { /* joint limits (only when violated) */
+    for (int side = 0; side < 2; ++side) {
+      double pen = side == 0 ? s->q[j] - m->lo[j] : m->hi[j] - s->q[j];
+      if (pen > 0) continue;
+      Row* r = &rows[nr++];
+      memset(r, 0, sizeof(*r));
+      r->J[j] = side == 0 ? 1 : -1;
+      apply_minv(e, Lm, Ibinv, r->J, r->W);
+      r->inv_diag = 1.0 / fabs(r->W[j]);
+      double rel = r->J[j] * u[j];
+      r->rhs = (-pen * m->P[MP_ERP_JOINT] / dt - rel) * r->inv_diag;
+      r->lo = 0; r->hi = m->P[MP_JOINT_LIMIT_IMPULSE]; r->friction_of = -1;
+    }
+  }
+  const int n_noncontact = nr;
+  Contact C[MAX_CONTACTS];
+  int nc = find_contacts(e, s, &k, C);
+  int normal_row[MAX_CONTACTS];
+  for (int ci = 0; ci < nc; ++ci) { /* normal rows */
+    Row* r = &rows[nr];
+    memset(r, 0, sizeof(*r));
+    contact_jacobian(e, s, &k, &C[ci], C[ci].n, r->J);
+    apply_minv(e, Lm, Ibinv, r->J, r->W);
+    r->inv_diag = 1.0 / dotn(r->J, r->W, NU);
+    double rel = dotn(r->J, u, NU);
+    double pen = C[ci].dist + m->P[MP_LINEAR_SLOP];
+    double pos_err = 0, vel_err = -rel;
+    if (pen > 0) vel_err -= pen / dt; else pos_err = -pen * m->P[MP_ERP_CONTACT] / dt;
+    r->rhs = (pos_err + vel_err) * r->inv_diag;
+    r->lo = 0; r->hi = 1e10; r->friction_of = -1;
+    normal_row[ci] = nr++;
+  }
+  const int n_normal_end = nr;
+  for (int ci = 0; ci < nc; ++ci) { /* two friction rows per contact, coupled by a cone */
+    double t1[3], t2[3];
+    plane_space(C[ci].n, t1, t2);
+    for (int d = 0; d < 2; ++d) {
+      Row* r = &rows[nr++];
+      memset(r, 0, sizeof(*r));
+      contact_jacobian(e, s, &k, &C[ci], d == 0 ? t1 : t2, r->J);
+      apply_minv(e, Lm, Ibinv, r->J, r->W);
+      r->inv_diag = 1.0 / dotn(r->J, r->W, NU);
+      r->rhs = -dotn(r->J, u, NU) * r->inv_diag;
+      r->friction_of = normal_row[ci]; r->mu = C[ci].mu;
+    }
+  }
+  /* ---- projected Gauss-Seidel (Bullet order: non-contact, normals, friction cones) ---- */
+  double dv[NU] = {0};
+  const int max_it = (int)m->P[MP_SOLVER_ITERS];
+  int it;
+  for (it = 0; it < max_it; ++it) {
+    double resid = 0;
+    for (int ri = 0; ri < n_normal_end; ++ri) {
+      Row* r = &rows[ri];
+      double d = r->rhs - dotn(r->J, dv, NU) * r->inv_diag;
+      double sum = r->lambda + d;
+      if (sum < r->lo) { d = r->lo - r->lambda; sum = r->lo; }
+      else if (sum > r->hi) { d = r->hi - r->lambda; sum = r->hi; }
+      r->lambda = sum;
+      for (int a = 0; a < NU; ++a) dv[a] += r->W[a] * d;
+      double res = d / r->inv_diag;
+      if (res * res > resid) resid = res * res;
+    }
+    for (int ri = n_normal_end; ri < nr; ri += 2) {
+      Row *ra = &rows[ri], *rb = &rows[ri + 1];
+      double lim = ra->mu * rows[ra->friction_of].lambda;
+      double da = ra->rhs - dotn(ra->J, dv, NU) * ra->inv_diag;
+      double db = rb->rhs - dotn(rb->J, dv, NU) * rb->inv_diag;
+      double sa = ra->lambda + da, sb = rb->lambda + db;
+      double nrm = sqrt(sa * sa + sb * sb);
+      if (nrm > lim) { double sc = nrm > 0 ? lim / nrm : 0; sa *= sc; sb *= sc; }
+      da = sa - ra->lambda; db = sb - rb->lambda;
+      ra->lambda = sa; rb->lambda = sb;
+      for (int a = 0; a < NU; ++a) dv[a] += ra->W[a] * da + rb->W[a] * db;
+      double r1 = da / ra->inv_diag, r2 = db / rb->inv_diag;
+      if (r1 * r1 > resid) resid = r1 * r1;
+      if (r2 * r2 > resid) resid = r2 * r2;
+    }
+    if (resid <= m->P[MP_RESIDUAL_THRESH]) { ++it; break; }
+  }
+  e->last_rows = nr; e->last_iters = it; e->last_contacts = nc;
+  (void)n_noncontact;
+  /* ---- integrate ---- */
+  for (int i = 0; i < NL; ++i) { s->qd[i] = u[i] + dv[i]; s->q[i] += dt * s->qd[i]; }
+  for (int a = 0; a < 3; ++a) { s->bv[a] = u[9 + a] + dv[9 + a]; s->bw[a] = u[12 + a] + dv[12 + a]; s->bp[a] += dt * s->bv[a]; }
+  { /* quaternion exponential map (btTransformUtil::integrateTransform) */
+    double wn = v3norm(s->bw), ax[3], th = wn * dt;
+    if (wn < 1e-12) { ax[0] = s->bw[0] * 0.5 * dt; ax[1] = s->bw[1] * 0.5 * dt; ax[2] = s->bw[2] * 0.5 * dt; }
+    else { double sc = sin(0.5 * th) / wn; ax[0] = s->bw[0] * sc; ax[1] = s->bw[1] * sc; ax[2] = s->bw[2] * sc; }
+    double dq[4] = {ax[0], ax[1], ax[2], cos(0.5 * th)}, q0[4] = {s->bq[0], s->bq[1], s->bq[2], s->bq[3]};
+    double r[4];
+    r[3] = dq[3] * q0[3] - dq[0] * q0[0] - dq[1] * q0[1] - dq[2] * q0[2];
+    r[0] = dq[3] * q0[0] + dq[0] * q0[3] + dq[1] * q0[2] - dq[2] * q0[1];
+    r[1] = dq[3] * q0[1] - dq[0] * q0[2] + dq[1] * q0[3] + dq[2] * q0[0];
+    r[2] = dq[3] * q0[2] + dq[0] * q0[1] - dq[1] * q0[0] + dq[2] * q0[3];
+    double nn = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+    for (int a = 0; a < 4; ++a) s->bq[a] = r[a] / nn;
+  }
+}
+
+/* ------------------------------------------------------------------ observation (27 floats) */
+static void observe(const Env* e, const State* s, double* obs, double* ag) {
+  const Model* m = &e->m;
+  Kin k;
+  fk(m, s->q, &k);
+  int ee = (int)m->P[MP_EE_LINK];
+  double w[3] = {0, 0, 0}, vo[3] = {0, 0, 0};
+  /* velocity of the EE link: accumulate along the chain */
+  int chain[NL], n = 0;
+  for (int i = ee; i >= 0; i = m->parent[i]) chain[n++] = i;
+  double pprev[3] = {0, 0, 0};
+  int first = 1;
+  for (int c = n - 1; c >= 0; --c) {
+    int i = chain[c];
+    if (!first) { double r[3], t[3]; v3sub(r, k.p[i], pprev); v3cross(t, w, r); v3add(vo, vo, t); }
+    v3axpy(w, s->qd[i], k.z[i]);
+    v3cpy(pprev, k.p[i]);
+    first = 0;
+  }
+  double rc[3], t[3], vcom[3], eul[3];
+  v3sub(rc, k.c[ee], k.p[ee]);
+  v3cross(t, w, rc);
+  v3add(vcom, vo, t); /* PyBullet reports the link velocity at the COM */
+  mat_to_euler(eul, k.R[ee]);
+  for (int a = 0; a < 3; ++a) {
+    obs[a] = k.p[ee][a];
+    obs[3 + a] = eul[a];
+    obs[6 + a] = vcom[a];
+    obs[9 + a] = w[a];
+    obs[12 + a] = s->bp[a];
+    obs[15 + a] = eul[a]; /* the reference's blockOrn slot repeats the gripper euler (push_F.py:188) */
+    obs[18 + a] = s->bp[a] - k.p[ee][a];
+    obs[21 + a] = s->bv[a];
+    obs[24 + a] = s->bw[a];
+    ag[a] = s->bp[a];
+  }
+}
+
+/* ------------------------------------------------------------------ public API (ctypes) */
+typedef struct { Env env; State st; } Handle;
+
+void* bmo_create(const float* blob, int64_t n, int task) {
+  Handle* h = (Handle*)calloc(1, sizeof(Handle));
+  if (load_model(&h->env.m, blob, n) != 0) { free(h); return NULL; }
+  h->env.task = task;
+  const double* P = h->env.m.P;
+  int o = task == 0 ? MP_PUSH_HX : MP_PICK_HX;
+  for (int a = 0; a < 3; ++a) h->env.bh[a] = P[o + a];
+  h->env.bmass = P[o + 3];
+  h->env.bmu = P[o + 4];
+  double lx = 2 * h->env.bh[0], ly = 2 * h->env.bh[1], lz = 2 * h->env.bh[2], mm = h->env.bmass / 12.0;
+  h->env.binertia[0] = mm * (ly * ly + lz * lz);
+  h->env.binertia[1] = mm * (lx * lx + lz * lz);
+  h->env.binertia[2] = mm * (lx * lx + ly * ly);
+  h->st.bq[3] = 1;
+  return h;
+}
+void bmo_destroy(void* hp) { free(hp); }
+void bmo_set_param(void* hp, int idx, double v) { ((Handle*)hp)->env.m.P[idx] = v; }
+double bmo_get_param(void* hp, int idx) { return ((Handle*)hp)->env.m.P[idx]; }
+
+/* init8 = block x,y,z,yaw, goal x,y,z, unused   (bmirobot_env_push_F.py:113-160) */
+void bmo_reset(void* hp, const double* init8, double* obs, double* ag, double* g) {
+  Handle* h = (Handle*)hp;
+  State* s = &h->st;
+  memset(s, 0, sizeof(*s));
+  v3set(s->bp, init8[0], init8[1], init8[2]);
+  s->bq[2] = sin(0.5 * init8[3]); s->bq[3] = cos(0.5 * init8[3]);
+  v3set(s->goal, init8[4], init8[5], init8[6]);
+  observe(&h->env, s, obs, ag);
+  v3cpy(g, s->goal);
+}
+
+void bmo_step(void* hp, const double* action, double* obs, double* ag, double* reward, double* success) {
+  Handle* h = (Handle*)hp;
+  Env* e = &h->env;
+  State* s = &h->st;
+  const Model* m = &e->m;
+  double a[4];
+  for (int i = 0; i < 4; ++i) a[i] = fmin(fmax(action[i], -0.5), 0.5);
+  if (e->task == 0) a[3] = 0; /* push: bmirobot_env_push_F.py:94 */
+  Kin k;
+  fk(m, s->q, &k);
+  int ee = (int)m->P[MP_EE_LINK];
+  if (e->task == 1) { /* pick: auto-grip when any arm shape is within 1e-4 of the block (pickandplace_v2.py:94-95) */
+    Contact C[MAX_CONTACTS];
+    double save = e->m.P[MP_BLOCK_MARGIN];
+    e->m.P[MP_BLOCK_MARGIN] = 1e-4;
+    int nc = find_contacts(e, s, &k, C);
+    e->m.P[MP_BLOCK_MARGIN] = save;
+    for (int i = 0; i < nc; ++i) if (C[i].has_block && C[i].link >= 0 && C[i].dist < 1e-4) { a[3] = -1; break; }
+  }
+  /* applyAction (bmirobot.py:129-162) */
+  double target[3] = {fmin(fmax(k.p[ee][0] + a[0], -1.0), 1.0), fmin(fmax(k.p[ee][1] + a[1], -1.0), 1.0),
+                      fmin(fmax(k.p[ee][2] + a[2], 0.0), 1.0)};
+  double qik[NL];
+  solve_ik(m, s->q, target, qik);
+  for (int j = 0; j < 7; ++j) s->qt[j] = qik[j];
+  s->qt[7] = s->q[7] + a[3]; /* sent_hand_moving (bmirobot.py:163-191) */
+  s->qt[8] = s->q[8] - a[3];
+  int nsub = (int)m->P[MP_N_SUBSTEPS];
+  for (int i = 0; i < nsub; ++i) substep(e, s);
+  observe(e, s, obs, ag);
+  double d[3];
+  v3sub(d, ag, s->goal);
+  double dist = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+  *success = dist < m->P[MP_DIST_THRESHOLD] ? 1.0 : 0.0;
+  *reward = dist > m->P[MP_DIST_THRESHOLD] ? -1.0 : -0.0;
+}
+
+void bmo_get_state(void* hp, double* st48) {
+  State* s = &((Handle*)hp)->st;
+  memset(st48, 0, sizeof(double) * 48);
+  memcpy(st48 + ST_Q, s->q, sizeof(s->q)); memcpy(st48 + ST_QD, s->qd, sizeof(s->qd)); memcpy(st48 + ST_QT, s->qt, sizeof(s->qt));
+  memcpy(st48 + ST_BPOS, s->bp, 24); memcpy(st48 + ST_BQUAT, s->bq, 32); memcpy(st48 + ST_BVEL, s->bv, 24);
+  memcpy(st48 + ST_BANG, s->bw, 24); memcpy(st48 + ST_GOAL, s->goal, 24);
+}
+void bmo_set_state(void* hp, const double* st48) {
+  State* s = &((Handle*)hp)->st;
+  memcpy(s->q, st48 + ST_Q, sizeof(s->q)); memcpy(s->qd, st48 + ST_QD, sizeof(s->qd)); memcpy(s->qt, st48 + ST_QT, sizeof(s->qt));
+  memcpy(s->bp, st48 + ST_BPOS, 24); memcpy(s->bq, st48 + ST_BQUAT, 32); memcpy(s->bv, st48 + ST_BVEL, 24);
+  memcpy(s->bw, st48 + ST_BANG, 24); memcpy(s->goal, st48 + ST_GOAL, 24);
+}
+void bmo_stats(void* hp, int* out3) {
+  Env* e = &((Handle*)hp)->env;
+  out3[0] = e->last_rows; out3[1] = e->last_iters; out3[2] = e->last_contacts;
+}
+/* expose pieces for unit tests */
+void bmo_ik(void* hp, const double* q0, const double* target, double* qout) { solve_ik(&((Handle*)hp)->env.m, q0, target, qout); }
+void bmo_fk_ee(void* hp, const double* q, double* pos3, double* euler3) {
+  Kin k;
+  fk(&((Handle*)hp)->env.m, q, &k);
+  int ee = (int)((Handle*)hp)->env.m.P[MP_EE_LINK];
+  v3cpy(pos3, k.p[ee]);
+  mat_to_euler(euler3, k.R[ee]);
+}
+void bmo_mass_matrix(void* hp, const double* q, double* M81) {
+  const Model* m = &((Handle*)hp)->env.m;
+  Kin k;
+  fk(m, q, &k);
+  double zero[NL] = {0}, ej[NL], col[NL];
+  for (int j = 0; j < NL; ++j) {
+    memset(ej, 0, sizeof(ej)); ej[j] = 1;
+    rnea(m, &k, zero, ej, 0, 0, 0, col);
+    for (int i = 0; i < NL; ++i) M81[i * NL + j] = col[i];
+  }
+}

@@ -57,8 +57,8 @@ SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p]),
     "bmi_her_draw": (c_int32, [c_uint64, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
-    "bmi_norm_update": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                  c_void_p]),
+    "bmi_norm_update": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_double, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
     "bmi_norm_recompute": (c_int32, [c_void_p] * 8 + [c_int32, c_float, c_float, c_void_p]),
     "bmi_norm_normalize": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                      c_double, c_void_p, c_int32, c_void_p]),

@@ -13,10 +13,14 @@ namespace bmi {
 
 // one thread per column; rows are consumed in order so the sum matches numpy exactly.
 template <typename T>
-__global__ void norm_update_kernel(const T* __restrict__ v, int64_t n_rows, int size,
+__global__ void norm_update_kernel(const T* __restrict__ vin, int64_t n_rows, int size, double clip,
                                    float* __restrict__ lsum, float* __restrict__ lsumsq,
                                    float* __restrict__ lcount) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  struct Clipped {  // np.clip(v, -clip, clip) on load
+    const T* p; double c;
+    __device__ double operator[](int64_t i) const { return fmin(fmax((double)p[i], -c), c); }
+  } v{vin, clip};
   if (j < size && n_rows > 0) {
     double s = (double)v[j];
     double q = __dmul_rn(s, s);
@@ -107,17 +111,18 @@ __global__ void preproc_inputs_kernel(const T* __restrict__ obs, const T* __rest
 
 using namespace bmi;
 
-extern "C" int bmi_norm_update(const void* v, int64_t n_rows, int32_t size, int32_t dtype,
+extern "C" int bmi_norm_update(const void* v, int64_t n_rows, int32_t size, int32_t dtype, double pre_clip,
                                float* lsum, float* lsumsq, float* lcount, bmi_stream_t stream) {
+  const double clip = pre_clip > 0.0 ? pre_clip : INFINITY;
   BMI_REQUIRE(size > 0 && n_rows >= 0, "bmi_norm_update: bad sizes");
   BMI_REQUIRE(dtype == BMI_F32 || dtype == BMI_F64, "bmi_norm_update: bad dtype %d", dtype);
   BMI_REQUIRE(lsum && lsumsq && lcount && (v || n_rows == 0), "bmi_norm_update: null pointer");
   unsigned grid = (unsigned)((size + 31) / 32);
   if (dtype == BMI_F64)
-    norm_update_kernel<double><<<grid, 32, 0, as_stream(stream)>>>((const double*)v, n_rows, size,
+    norm_update_kernel<double><<<grid, 32, 0, as_stream(stream)>>>((const double*)v, n_rows, size, clip,
                                                                    lsum, lsumsq, lcount);
   else
-    norm_update_kernel<float><<<grid, 32, 0, as_stream(stream)>>>((const float*)v, n_rows, size,
+    norm_update_kernel<float><<<grid, 32, 0, as_stream(stream)>>>((const float*)v, n_rows, size, clip,
                                                                   lsum, lsumsq, lcount);
   BMI_LAUNCHED();
   return BMI_OK;

@@ -1,0 +1,1006 @@
+// Vectorised bmirobot environment: one CUDA thread block (one warp) per env instance.
+//
+// Reference behaviour restated (paths relative to the reference tree; the arithmetic itself
+// lives in PyBullet, so the algorithm follows oracle/bmi_physics_oracle.c line for line):
+//   bmirobot_env/bmirobot_env_push_F.py:92-108   step: clip, action[3]=0, IK + motors, 20 sub-steps
+//   bmirobot_env/bmirobot_env_push_F.py:110-165  reset (block / goal placement ranges)
+//   bmirobot_env/bmirobot_env_push_F.py:169-237  27-float observation
+//   bmirobot_env/bmirobot.py:129-191             applyAction / sent_hand_moving
+//   bmirobot_env/bmirobot_inverse_kinematics.py:28-33  position-only DLS IK of link 11
+//   bmirobot_env/bmirobot_env_pickandplace_v2.py:92-95,116-131  pick task deltas
+//
+// Per sub-step: forward kinematics -> mass matrix + bias by 10 lane-parallel recursive
+// Newton-Euler sweeps (lane j < 9: unit acceleration e_j, lane 9: velocity/gravity/damping bias)
+// -> Cholesky -> unconstrained velocities -> contact generation (lane = vertex) -> constraint
+// rows (lane = row) -> projected Gauss-Seidel with warp-shuffle dot products (lane = generalized
+// velocity) -> semi-implicit Euler.  fp32 throughout, no tensor cores.
+// The kinematic tree + solver constants (header + 9 link records of the model blob, 1408 B) are
+// staged into shared memory by one TMA bulk copy per block; convex-polytope vertex/plane pools
+// are read through the read-only path (they are shared by every block and stay in L1/L2).
+#include "common.cuh"
+#include "../../include/bmi_model.h"
+
+namespace bmi {
+
+constexpr int NL = 9;          // links / joints of the right arm
+constexpr int NU = 15;         // generalized velocities: 9 joints + block linear 3 + angular 3
+constexpr int EE = 8;          // right_hand2
+constexpr int MAXC = 16;       // contacts per sub-step
+constexpr int MAXNC = 17;      // non-contact rows: 9 motors + up to 8 limit rows
+constexpr int MAXR = MAXNC + 3 * MAXC;
+constexpr int STAGED = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;  // floats staged by TMA
+constexpr unsigned FULL = 0xffffffffu;
+
+// topology of the right arm: chain 0..6, two fingers on link 6 (checked against the blob)
+__host__ __device__ constexpr int parent_of(int i) { return i == 0 ? -1 : (i <= 6 ? i - 1 : 6); }
+__host__ __device__ constexpr bool is_ancestor_or_self(int a, int l) {
+  return a == l || (a <= 6 && l >= a);  // every chain link j<=6 is an ancestor of all l>=j
+}
+
+struct __align__(16) Smem {
+  float model[STAGED];            // header params + link records (TMA destination)
+  unsigned long long mbar;
+  float R[NL][9], p[NL][3], z[NL][3], c[NL][3], Rl[NL][9];
+  float L[NL * NL], Minv[NL * NL];
+  float q[NL], qd[NL], qt[NL], bias[NL], acc[NL];
+  float u[16];
+  float bp[3], bq[4], bv[3], bw[3], goal[3];
+  float Rb[9], Ibinv[9], bvert[8][3];
+  // contacts
+  float cx[MAXC][3], cn[MAXC][3], cdist[MAXC], cmu[MAXC];
+  int clink[MAXC], chasb[MAXC];
+  int nc;
+  // rows
+  float J[3 * MAXC][16], W[3 * MAXC][16];
+  float invd[MAXR], rhs[MAXR], lo[MAXR], hi[MAXR], lam[MAXR];
+  int ncj[MAXNC];                 // joint index (+1, sign = direction) of each non-contact row
+  // IK scratch
+  float A[NL * NL], b[NL], qik[NL];
+};
+
+struct EnvParams {
+  int task;
+  float bh[3], bmass, binertia[3], bmu;
+};
+
+__device__ __forceinline__ float P(const Smem& s, int i) { return s.model[i]; }
+__device__ __forceinline__ const float* LK(const Smem& s, int i) { return s.model + BMI_MODEL_HDR + i * BMI_LINK_STRIDE; }
+
+__device__ __forceinline__ void cross3(float* o, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void mat_vec(float* o, const float* A, const float* v) {
+  float x = A[0] * v[0] + A[1] * v[1] + A[2] * v[2], y = A[3] * v[0] + A[4] * v[1] + A[5] * v[2],
+        z = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ void matT_vec(float* o, const float* A, const float* v) {
+  float x = A[0] * v[0] + A[3] * v[1] + A[6] * v[2], y = A[1] * v[0] + A[4] * v[1] + A[7] * v[2],
+        z = A[2] * v[0] + A[5] * v[1] + A[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ float warp_sum16(float v) {  // sum over lanes 0..15 (butterfly), result in all 16
+  v += __shfl_xor_sync(FULL, v, 8);
+  v += __shfl_xor_sync(FULL, v, 4);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 1);
+  return v;
+}
+
+// ---- TMA staging of the joint tree ---------------------------------------------------------
+__device__ __forceinline__ void stage_model(Smem& s, const float* __restrict__ model_g, int lane) {
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s.mbar);
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(s.model);
+  constexpr unsigned bytes = STAGED * sizeof(float);
+  static_assert(bytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(model_g), "r"(bytes), "r"(mbar)
+                 : "memory");
+  }
+  __syncwarp();
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar)
+        : "memory");
+  }
+}
+
+// ---- forward kinematics ----------------------------------------------------------------------
+__device__ void fk(Smem& s, const float* q, int lane) {
+  if (lane < NL) {  // local rotation jrot * Rodrigues(axis, q)
+    const float* lk = LK(s, lane);
+    const float ux = lk[ML_AXIS], uy = lk[ML_AXIS + 1], uz = lk[ML_AXIS + 2];
+    float sn, cs;
+    sincosf(q[lane], &sn, &cs);
+    const float C = 1.f - cs;
+    float Rq[9] = {cs + ux * ux * C,      ux * uy * C - uz * sn, ux * uz * C + uy * sn,
+                   uy * ux * C + uz * sn, cs + uy * uy * C,      uy * uz * C - ux * sn,
+                   uz * ux * C - uy * sn, uz * uy * C + ux * sn, cs + uz * uz * C};
+    const float* Jr = lk + ML_JROT;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc)
+        s.Rl[lane][3 * r + cc] = Jr[3 * r] * Rq[cc] + Jr[3 * r + 1] * Rq[3 + cc] + Jr[3 * r + 2] * Rq[6 + cc];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int pa = parent_of(i);
+    if (lane < 9) {
+      const int r = lane / 3, cc = lane % 3;
+      float v;
+      if (pa < 0) v = s.Rl[i][lane];
+      else v = s.R[pa][3 * r] * s.Rl[i][cc] + s.R[pa][3 * r + 1] * s.Rl[i][3 + cc] + s.R[pa][3 * r + 2] * s.Rl[i][6 + cc];
+      s.R[i][lane] = v;
+    } else if (lane < 12) {
+      const int a = lane - 9;
+      const float* jp = LK(s, i) + ML_JPOS;
+      float v;
+      if (pa < 0) v = P(s, MP_BASE_PX + a) + jp[a];
+      else v = s.p[pa][a] + s.R[pa][3 * a] * jp[0] + s.R[pa][3 * a + 1] * jp[1] + s.R[pa][3 * a + 2] * jp[2];
+      s.p[i][a] = v;
+    }
+    __syncwarp();
+  }
+  if (lane < NL) {
+    const float* lk = LK(s, lane);
+    float t[3];
+    mat_vec(t, s.R[lane], lk + ML_AXIS);
+    s.z[lane][0] = t[0]; s.z[lane][1] = t[1]; s.z[lane][2] = t[2];
+    mat_vec(t, s.R[lane], lk + ML_COM);
+    s.c[lane][0] = s.p[lane][0] + t[0]; s.c[lane][1] = s.p[lane][1] + t[1]; s.c[lane][2] = s.p[lane][2] + t[2];
+  }
+  __syncwarp();
+}
+
+// ---- recursive Newton-Euler, one independent sweep per lane ------------------------------------
+// tau_j = z_j . sum_{k in subtree(j)} [ N_k + (c_k - p_j) x F_k ]   (accumulated pairwise so that no
+// per-link force arrays are needed; the tree topology is a compile-time constant).
+template <bool kBias>
+__device__ __forceinline__ void rnea_lane(const Smem& s, const float* qd, int unit, float gz, float kl, float ka,
+                                          float* tau) {
+  float w[3] = {0, 0, 0}, al[3] = {0, 0, 0}, a[3] = {0, 0, -gz}, vo[3] = {0, 0, 0};
+  float w6[3], al6[3], a6[3], vo6[3];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) tau[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    const int pa = parent_of(i);
+    if (i == 7 || i == 8) {  // fingers hang off link 6
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { w[k] = w6[k]; al[k] = al6[k]; a[k] = a6[k]; vo[k] = vo6[k]; }
+    }
+    float t[3], t2[3];
+    if (pa >= 0) {
+      float r[3] = {s.p[i][0] - s.p[pa][0], s.p[i][1] - s.p[pa][1], s.p[i][2] - s.p[pa][2]};
+      if (kBias) { cross3(t, w, r); vo[0] += t[0]; vo[1] += t[1]; vo[2] += t[2]; }
+      cross3(t, al, r);
+      a[0] += t[0]; a[1] += t[1]; a[2] += t[2];
+      if (kBias) { cross3(t, w, r); cross3(t2, w, t); a[0] += t2[0]; a[1] += t2[1]; a[2] += t2[2]; }
+    }
+    const float qdi = kBias ? qd[i] : 0.f;
+    const float qddi = (!kBias && unit == i) ? 1.f : 0.f;
+    const float* zi = s.z[i];
+    if (kBias) { cross3(t, w, zi); al[0] += qdi * t[0]; al[1] += qdi * t[1]; al[2] += qdi * t[2]; }
+    al[0] += qddi * zi[0]; al[1] += qddi * zi[1]; al[2] += qddi * zi[2];
+    if (kBias) { w[0] += qdi * zi[0]; w[1] += qdi * zi[1]; w[2] += qdi * zi[2]; }
+    if (i == 6) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { w6[k] = w[k]; al6[k] = al[k]; a6[k] = a[k]; vo6[k] = vo[k]; }
+    }
+    const float* lk = LK(s, i);
+    const float mass = lk[ML_MASS];
+    float rc[3] = {s.c[i][0] - s.p[i][0], s.c[i][1] - s.p[i][1], s.c[i][2] - s.p[i][2]};
+    float ac[3];
+    cross3(t, al, rc);
+    ac[0] = a[0] + t[0]; ac[1] = a[1] + t[1]; ac[2] = a[2] + t[2];
+    float F[3], N[3];
+    if (kBias) {
+      cross3(t, w, rc); cross3(t2, w, t);
+      ac[0] += t2[0]; ac[1] += t2[1]; ac[2] += t2[2];
+      float vc[3] = {vo[0] + t[0], vo[1] + t[1], vo[2] + t[2]};
+      const float vn = sqrtf(dot3(vc, vc));
+      const float kd = mass * (kl + kl * vn);
+      F[0] = mass * ac[0] + kd * vc[0]; F[1] = mass * ac[1] + kd * vc[1]; F[2] = mass * ac[2] + kd * vc[2];
+    } else {
+      F[0] = mass * ac[0]; F[1] = mass * ac[1]; F[2] = mass * ac[2];
+    }
+    {
+      float ll[3], tl[3];
+      matT_vec(ll, s.R[i], al);
+      tl[0] = lk[ML_INERTIA] * ll[0]; tl[1] = lk[ML_INERTIA + 1] * ll[1]; tl[2] = lk[ML_INERTIA + 2] * ll[2];
+      mat_vec(N, s.R[i], tl);
+      if (kBias) {
+        float wl[3], Iw[3];
+        matT_vec(wl, s.R[i], w);
+        tl[0] = lk[ML_INERTIA] * wl[0]; tl[1] = lk[ML_INERTIA + 1] * wl[1]; tl[2] = lk[ML_INERTIA + 2] * wl[2];
+        mat_vec(Iw, s.R[i], tl);
+        cross3(t, w, Iw);
+        const float wn = sqrtf(dot3(w, w));
+        const float kk = ka + ka * wn;
+        N[0] += t[0] + kk * Iw[0]; N[1] += t[1] + kk * Iw[1]; N[2] += t[2] + kk * Iw[2];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      if (is_ancestor_or_self(j, i)) {
+        float r[3] = {s.c[i][0] - s.p[j][0], s.c[i][1] - s.p[j][1], s.c[i][2] - s.p[j][2]};
+        cross3(t, r, F);
+        tau[j] += s.z[j][0] * (N[0] + t[0]) + s.z[j][1] * (N[1] + t[1]) + s.z[j][2] * (N[2] + t[2]);
+      }
+    }
+  }
+}
+
+// Cholesky of the 9x9 SPD matrix in s.L (lower, in place); lanes cooperate per column.
+__device__ void chol9(float* Lm, int lane) {
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    float d = 0.f;
+    if (lane == 0) {
+      d = Lm[j * NL + j];
+      for (int k = 0; k < j; ++k) d -= Lm[j * NL + k] * Lm[j * NL + k];
+      d = sqrtf(fmaxf(d, 1e-20f));
+      Lm[j * NL + j] = d;
+    }
+    d = __shfl_sync(FULL, d, 0);
+    if (lane > j && lane < NL) {
+      float sacc = Lm[lane * NL + j];
+      for (int k = 0; k < j; ++k) sacc -= Lm[lane * NL + k] * Lm[j * NL + k];
+      Lm[lane * NL + j] = sacc / d;
+    }
+    __syncwarp();
+  }
+}
+// per-lane triangular solves  L L^T x = b   (b, x: 9 registers)
+__device__ __forceinline__ void chol9_solve(const float* Lm, const float* b, float* x) {
+  float y[NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    float sacc = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) sacc -= Lm[i * NL + k] * y[k];
+    y[i] = sacc / Lm[i * NL + i];
+  }
+#pragma unroll
+  for (int i = NL - 1; i >= 0; --i) {
+    float sacc = y[i];
+#pragma unroll
+    for (int k = i + 1; k < NL; ++k) sacc -= Lm[k * NL + i] * x[k];
+    x[i] = sacc / Lm[i * NL + i];
+  }
+}
+
+// ---- inverse kinematics (BussIK DLS restated, see oracle solve_ik) ------------------------------
+__device__ void solve_ik(Smem& s, const float* target, int lane) {
+  if (lane < NL) s.qik[lane] = s.q[lane];
+  __syncwarp();
+  const int iters = (int)P(s, MP_IK_ITERS);
+  const float damp = P(s, MP_IK_DAMPING), thr = P(s, MP_IK_THRESH), maxang = P(s, MP_IK_MAX_ANGLE);
+  for (int it = 0; it < iters; ++it) {
+    fk(s, s.qik, lane);
+    float e[3] = {target[0] - s.p[EE][0], target[1] - s.p[EE][1], target[2] - s.p[EE][2]};
+    if (sqrtf(dot3(e, e)) <= thr) break;  // uniform across the warp
+    // Jacobian column of joint `lane` (joint 7 is not on the path to the EE)
+    float Jc[3] = {0, 0, 0};
+    if (lane < NL && lane != 7) {
+      float r[3] = {s.p[EE][0] - s.p[lane][0], s.p[EE][1] - s.p[lane][1], s.p[EE][2] - s.p[lane][2]};
+      cross3(Jc, s.z[lane], r);
+    }
+    // A = J^T J + damp I, b = J^T e ; lane i owns row i
+    float Arow[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      float jx = __shfl_sync(FULL, Jc[0], j), jy = __shfl_sync(FULL, Jc[1], j), jz = __shfl_sync(FULL, Jc[2], j);
+      Arow[j] = Jc[0] * jx + Jc[1] * jy + Jc[2] * jz + ((j == lane) ? damp : 0.f);
+    }
+    if (lane < NL) {
+#pragma unroll
+      for (int j = 0; j < NL; ++j) s.A[lane * NL + j] = Arow[j];
+      s.b[lane] = Jc[0] * e[0] + Jc[1] * e[1] + Jc[2] * e[2];
+    }
+    __syncwarp();
+    chol9(s.A, lane);
+    float bb[NL], x[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) bb[j] = s.b[j];
+    chol9_solve(s.A, bb, x);  // every lane solves the same system (cheap, avoids a broadcast)
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) mx = fmaxf(mx, fabsf(x[j]));
+    const float sc = mx > maxang ? maxang / mx : 1.f;
+    __syncwarp();
+    if (lane < NL) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) if (j == lane) v = x[j];
+      s.qik[lane] += sc * v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- contact generation ---------------------------------------------------------------------------
+// keep the `cap` lanes with the smallest d (< margin); ties resolved towards the lower lane; returns the
+// ballot mask of the selected lanes
+__device__ __forceinline__ unsigned select_deepest(float d, bool valid, float margin, int cap, int lane) {
+  unsigned picked = 0;
+  bool cand = valid && d < margin;
+  for (int r = 0; r < cap; ++r) {
+    float v = cand ? d : 3.0e38f;
+    int idx = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(FULL, v, o);
+      int oi = __shfl_xor_sync(FULL, idx, o);
+      if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if (v >= 3.0e38f) break;
+    picked |= 1u << idx;
+    if (lane == idx) cand = false;
+  }
+  return picked;
+}
+
+__device__ __forceinline__ void push_contacts(Smem& s, unsigned mask, int lane, int link, int hasb, const float* x,
+                                              const float* n, float dist, float mu) {
+  if (mask == 0) return;
+  const int base = s.nc;
+  const int slot = base + __popc(mask & ((1u << lane) - 1));
+  if ((mask >> lane) & 1u) {
+    if (slot < MAXC) {
+      s.cx[slot][0] = x[0]; s.cx[slot][1] = x[1]; s.cx[slot][2] = x[2];
+      s.cn[slot][0] = n[0]; s.cn[slot][1] = n[1]; s.cn[slot][2] = n[2];
+      s.cdist[slot] = dist; s.cmu[slot] = mu; s.clink[slot] = link; s.chasb[slot] = hasb;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) s.nc = min(MAXC, base + __popc(mask));
+  __syncwarp();
+}
+
+__device__ void find_contacts(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, float block_margin,
+                              int lane) {
+  if (lane == 0) s.nc = 0;
+  // block frame
+  if (lane == 0) {
+    const float x = s.bq[0], y = s.bq[1], z = s.bq[2], w = s.bq[3];
+    s.Rb[0] = 1 - 2 * (y * y + z * z); s.Rb[1] = 2 * (x * y - z * w);     s.Rb[2] = 2 * (x * z + y * w);
+    s.Rb[3] = 2 * (x * y + z * w);     s.Rb[4] = 1 - 2 * (x * x + z * z); s.Rb[5] = 2 * (y * z - x * w);
+    s.Rb[6] = 2 * (x * z - y * w);     s.Rb[7] = 2 * (y * z + x * w);     s.Rb[8] = 1 - 2 * (x * x + y * y);
+  }
+  __syncwarp();
+  const float tz = P(s, MP_TABLE_Z);
+  float bvx[3] = {0, 0, 0};
+  if (lane < 8) {
+    float l[3] = {(lane & 1 ? 1.f : -1.f) * ep.bh[0], (lane & 2 ? 1.f : -1.f) * ep.bh[1], (lane & 4 ? 1.f : -1.f) * ep.bh[2]};
+    mat_vec(bvx, s.Rb, l);
+    bvx[0] += s.bp[0]; bvx[1] += s.bp[1]; bvx[2] += s.bp[2];
+    s.bvert[lane][0] = bvx[0]; s.bvert[lane][1] = bvx[1]; s.bvert[lane][2] = bvx[2];
+  }
+  __syncwarp();
+  const float up[3] = {0.f, 0.f, 1.f};
+  {  // block vertices vs table plane, up to 4 deepest
+    const float d = bvx[2] - tz;
+    unsigned m = select_deepest(d, lane < 8, P(s, MP_TABLE_MARGIN), 4, lane);
+    push_contacts(s, m, lane, -1, 1, bvx, up, d, ep.bmu * P(s, MP_MU_TABLE));
+  }
+  const int ns = (int)P(s, MP_N_SHAPES);
+  const float* shapes = model_g + (int)P(s, MP_SHAPES_OFF);
+  const float* pool = model_g + (int)P(s, MP_POOL_OFF);
+  const float brad = sqrtf(ep.bh[0] * ep.bh[0] + ep.bh[1] * ep.bh[1] + ep.bh[2] * ep.bh[2]);
+  for (int si = 0; si < ns; ++si) {
+    const float* sh = shapes + si * BMI_SHAPE_STRIDE;
+    const int l = (int)__ldg(sh + MS_LINK), nv = (int)__ldg(sh + MS_NVERTS), np = (int)__ldg(sh + MS_NPLANES);
+    const float* verts = pool + (int)__ldg(sh + MS_VERT_OFF);
+    const float* planes = pool + (int)__ldg(sh + MS_PLANE_OFF);
+    const float smu = __ldg(sh + MS_MU);
+    float wv[3] = {0, 0, 0};
+    if (lane < nv) {
+      float lv[3] = {__ldg(verts + 3 * lane), __ldg(verts + 3 * lane + 1), __ldg(verts + 3 * lane + 2)};
+      mat_vec(wv, s.R[l], lv);
+      wv[0] += s.p[l][0]; wv[1] += s.p[l][1]; wv[2] += s.p[l][2];
+    }
+    {  // hull vertices vs table plane, up to 2 deepest
+      const float d = wv[2] - tz;
+      unsigned m = select_deepest(d, lane < nv, P(s, MP_CONTACT_MARGIN), 2, lane);
+      push_contacts(s, m, lane, l, 0, wv, up, d, smu * P(s, MP_MU_TABLE));
+    }
+    // broadphase: bounding spheres
+    float lc[3] = {__ldg(sh + MS_SPHERE_C), __ldg(sh + MS_SPHERE_C + 1), __ldg(sh + MS_SPHERE_C + 2)}, cw[3];
+    mat_vec(cw, s.R[l], lc);
+    float dd[3] = {s.bp[0] - cw[0] - s.p[l][0], s.bp[1] - cw[1] - s.p[l][1], s.bp[2] - cw[2] - s.p[l][2]};
+    if (sqrtf(dot3(dd, dd)) > __ldg(sh + MS_SPHERE_R) + brad + block_margin) continue;  // uniform
+    // candidates: lanes 0..7 = block vertex vs hull planes, lanes 8..8+nv-1 = hull vertex vs block box
+    float d = 3.0e38f, nrm[3] = {0, 0, 0}, x[3] = {0, 0, 0};
+    bool valid = false;
+    if (lane < 8) {
+      float r[3] = {bvx[0] - s.p[l][0], bvx[1] - s.p[l][1], bvx[2] - s.p[l][2]}, xl[3];
+      matT_vec(xl, s.R[l], r);
+      float best = -1e30f;
+      int bpi = 0;
+      for (int pi = 0; pi < np; ++pi) {
+        const float4 pl = __ldg(reinterpret_cast<const float4*>(planes) + pi);
+        const float sd = pl.x * xl[0] + pl.y * xl[1] + pl.z * xl[2] + pl.w;
+        if (sd > best) { best = sd; bpi = pi; }
+      }
+      const float4 pl = __ldg(reinterpret_cast<const float4*>(planes) + bpi);
+      float ln[3] = {pl.x, pl.y, pl.z};
+      mat_vec(nrm, s.R[l], ln);
+      d = best; valid = true;
+      x[0] = bvx[0]; x[1] = bvx[1]; x[2] = bvx[2];
+    }
+    // hull vertices are owned by lanes 0..nv-1 but candidate slots are 8..8+nv-1: shift by 8 lanes
+    {
+      const int src = lane - 8;
+      float hx = __shfl_sync(FULL, wv[0], src & 31), hy = __shfl_sync(FULL, wv[1], src & 31), hz = __shfl_sync(FULL, wv[2], src & 31);
+      if (lane >= 8 && src < nv) {
+        float r[3] = {hx - s.bp[0], hy - s.bp[1], hz - s.bp[2]}, xb[3];
+        matT_vec(xb, s.Rb, r);
+        float best = -1e30f, sg = 1.f;
+        int ba = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float sd = fabsf(xb[a]) - ep.bh[a];
+          if (sd > best) { best = sd; ba = a; sg = xb[a] >= 0.f ? 1.f : -1.f; }
+        }
+        nrm[0] = -sg * s.Rb[ba]; nrm[1] = -sg * s.Rb[3 + ba]; nrm[2] = -sg * s.Rb[6 + ba];
+        d = best; valid = true;
+        x[0] = hx; x[1] = hy; x[2] = hz;
+      }
+    }
+    // (hull polytopes are baked with <= 24 vertices, so 8 + nv <= 32 candidates fit one warp)
+    unsigned m = select_deepest(d, valid, block_margin, 3, lane);
+    push_contacts(s, m, lane, l, 1, x, nrm, d, ep.bmu * smu);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void plane_space(const float* n, float* p, float* q) {
+  if (fabsf(n[2]) > 0.70710678f) {
+    const float a = n[1] * n[1] + n[2] * n[2], k = rsqrtf(a);
+    p[0] = 0.f; p[1] = -n[2] * k; p[2] = n[1] * k;
+    q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+  } else {
+    const float a = n[0] * n[0] + n[1] * n[1], k = rsqrtf(a);
+    p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0.f;
+    q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+  }
+}
+
+// ---- one simulation sub-step ------------------------------------------------------------------------
+__device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, int lane) {
+  const float dt = P(s, MP_DT), gz = P(s, MP_GRAVITY), kl = P(s, MP_LIN_DAMP), ka = P(s, MP_ANG_DAMP);
+  fk(s, s.q, lane);
+  {  // mass matrix columns (lanes 0..8) and bias (lane 9)
+    float tau[NL];
+    if (lane < NL) {
+      rnea_lane<false>(s, nullptr, lane, 0.f, 0.f, 0.f, tau);
+#pragma unroll
+      for (int i = 0; i < NL; ++i) s.L[i * NL + lane] = tau[i];
+    } else if (lane == 9) {
+      rnea_lane<true>(s, s.qd, -1, gz, kl, ka, tau);
+#pragma unroll
+      for (int i = 0; i < NL; ++i) s.bias[i] = tau[i];
+    }
+  }
+  __syncwarp();
+  if (lane < NL) {  // symmetrise (lower triangle is what Cholesky reads)
+    float v[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) v[j] = 0.5f * (s.L[lane * NL + j] + s.L[j * NL + lane]);
+    __syncwarp(0x1ff);
+#pragma unroll
+    for (int j = 0; j < NL; ++j) s.L[lane * NL + j] = v[j];
+  }
+  __syncwarp();
+  chol9(s.L, lane);
+  // M^-1 columns (lanes 0..8) and unconstrained acceleration (lane 9)
+  if (lane <= NL) {
+    float b[NL], x[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) b[i] = lane < NL ? (i == lane ? 1.f : 0.f) : (-LK(s, i)[ML_DAMPING] * s.qd[i] - s.bias[i]);
+    chol9_solve(s.L, b, x);
+    if (lane < NL) {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) s.Minv[i * NL + lane] = x[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) s.acc[i] = x[i];
+    }
+  }
+  __syncwarp();
+  // predicted (unconstrained) velocities
+  if (lane < NL) s.u[lane] = s.qd[lane] + dt * s.acc[lane];
+  else if (lane < 12) {
+    const int a = lane - 9;
+    const float vn = sqrtf(dot3(s.bv, s.bv));
+    s.u[lane] = s.bv[a] + dt * (-(kl + kl * vn) * s.bv[a]) + (a == 2 ? dt * gz : 0.f);
+  } else if (lane < 15) {
+    const int a = lane - 12;
+    const float wn = sqrtf(dot3(s.bw, s.bw));
+    s.u[lane] = s.bw[a] + dt * (-(ka + ka * wn) * s.bw[a]);
+  } else if (lane == 15) s.u[15] = 0.f;
+  find_contacts(s, ep, model_g, P(s, MP_BLOCK_MARGIN), lane);
+  if (lane < 9) {  // world-frame inverse inertia of the block: R diag(1/I) R^T
+    const int r = lane / 3, cc = lane % 3;
+    s.Ibinv[lane] = s.Rb[3 * r] * s.Rb[3 * cc] / ep.binertia[0] + s.Rb[3 * r + 1] * s.Rb[3 * cc + 1] / ep.binertia[1] +
+                    s.Rb[3 * r + 2] * s.Rb[3 * cc + 2] / ep.binertia[2];
+  }
+  __syncwarp();
+  // ---- non-contact rows: motors (always) then violated joint limits --------------------------------
+  const float max_imp = P(s, MP_MOTOR_FORCE) * dt;
+  int n_nc = NL;
+  if (lane < NL) {
+    const float w = s.Minv[lane * NL + lane];
+    const float target = P(s, MP_MOTOR_KP) * (s.qt[lane] - s.q[lane]) / dt + (1.f - P(s, MP_MOTOR_KD)) * s.qd[lane];
+    s.invd[lane] = 1.f / w;
+    s.rhs[lane] = (target - s.u[lane]) / w;
+    s.lo[lane] = -max_imp; s.hi[lane] = max_imp; s.lam[lane] = 0.f;
+    s.ncj[lane] = lane + 1;
+  }
+  {
+    // limit candidates: lane = 2*j + side
+    bool viol = false;
+    float pen = 0.f;
+    const int j = lane >> 1, side = lane & 1;
+    if (lane < 2 * NL) {
+      pen = side == 0 ? s.q[j] - LK(s, j)[ML_LO] : LK(s, j)[ML_HI] - s.q[j];
+      viol = !(pen > 0.f);
+    }
+    unsigned m = __ballot_sync(FULL, viol);
+    const int slot = NL + __popc(m & ((1u << lane) - 1));
+    if (viol && slot < MAXNC) {
+      const float sgn = side == 0 ? 1.f : -1.f;
+      const float w = s.Minv[j * NL + j];
+      s.invd[slot] = 1.f / w;
+      s.rhs[slot] = (-pen * P(s, MP_ERP_JOINT) / dt - sgn * s.u[j]) / w;
+      s.lo[slot] = 0.f; s.hi[slot] = P(s, MP_JOINT_LIMIT_IMPULSE); s.lam[slot] = 0.f;
+      s.ncj[slot] = side == 0 ? (j + 1) : -(j + 1);
+    }
+    n_nc = min(MAXNC, NL + __popc(m));
+  }
+  __syncwarp();
+  // ---- contact rows: lane = row (3 rows per contact: normal, tangent 1, tangent 2) ------------------
+  const int nc = s.nc;
+  const int n_rows_c = 3 * nc;
+  for (int base = 0; base < n_rows_c; base += 32) {
+    const int ri = base + lane;
+    if (ri < n_rows_c) {
+      const int ci = ri < nc ? ri : (ri - nc) / 2;
+      const int kind = ri < nc ? 0 : 1 + ((ri - nc) & 1);
+      float n[3] = {s.cn[ci][0], s.cn[ci][1], s.cn[ci][2]}, dir[3], t1[3], t2[3];
+      plane_space(n, t1, t2);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) dir[a] = kind == 0 ? n[a] : (kind == 1 ? t1[a] : t2[a]);
+      const float x[3] = {s.cx[ci][0], s.cx[ci][1], s.cx[ci][2]};
+      const int link = s.clink[ci], hasb = s.chasb[ci];
+      float J[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) J[a] = 0.f;
+      if (hasb) {
+        float r[3] = {x[0] - s.bp[0], x[1] - s.bp[1], x[2] - s.bp[2]}, t[3];
+        cross3(t, r, dir);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { J[9 + a] = dir[a]; J[12 + a] = t[a]; }
+      }
+      if (link >= 0) {
+        const float sgn = hasb ? -1.f : 1.f;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          // joint j moves `link` iff it lies on the path base -> link
+          const bool on = (j <= 6) ? (link >= j) : (link == j);
+          if (on) {
+            float r[3] = {x[0] - s.p[j][0], x[1] - s.p[j][1], x[2] - s.p[j][2]}, cr[3];
+            cross3(cr, s.z[j], r);
+            J[j] = sgn * dot3(dir, cr);
+          }
+        }
+      }
+      float Wv[NU];
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) acc += s.Minv[i * NL + j] * J[j];
+        Wv[i] = acc;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) Wv[9 + a] = J[9 + a] / ep.bmass;
+      mat_vec(Wv + 12, s.Ibinv, J + 12);
+      float diag = 0.f, rel = 0.f;
+#pragma unroll
+      for (int a = 0; a < NU; ++a) { diag += J[a] * Wv[a]; rel += J[a] * s.u[a]; }
+      const float invd = 1.f / diag;
+#pragma unroll
+      for (int a = 0; a < NU; ++a) { s.J[ri][a] = J[a]; s.W[ri][a] = Wv[a]; }
+      s.J[ri][15] = 0.f; s.W[ri][15] = 0.f;
+      const int row = MAXNC + ri;
+      s.invd[row] = invd; s.lam[row] = 0.f;
+      if (kind == 0) {
+        const float pen = s.cdist[ci] + P(s, MP_LINEAR_SLOP);
+        float pos_err = 0.f, vel_err = -rel;
+        if (pen > 0.f) vel_err -= pen / dt; else pos_err = -pen * P(s, MP_ERP_CONTACT) / dt;
+        s.rhs[row] = (pos_err + vel_err) * invd;
+        s.lo[row] = 0.f; s.hi[row] = 1e10f;
+      } else {
+        s.rhs[row] = -rel * invd;
+        s.lo[row] = 0.f; s.hi[row] = 0.f;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- projected Gauss-Seidel; lane d holds dv[d] -------------------------------------------------------
+  float dv = 0.f;
+  const int max_it = (int)P(s, MP_SOLVER_ITERS);
+  const float thresh = P(s, MP_RESIDUAL_THRESH);
+  for (int it = 0; it < max_it; ++it) {
+    float resid = 0.f;
+    for (int r = 0; r < n_nc; ++r) {  // motors / limits: J = +-e_j
+      const int jj = s.ncj[r];
+      const int j = abs(jj) - 1;
+      const float sgn = jj > 0 ? 1.f : -1.f;
+      const float invd = s.invd[r];
+      float d = s.rhs[r] - sgn * __shfl_sync(FULL, dv, j) * invd;
+      const float old = s.lam[r];
+      float sum = fminf(fmaxf(old + d, s.lo[r]), s.hi[r]);
+      d = sum - old;
+      s.lam[r] = sum;
+      if (lane < NL) dv += sgn * s.Minv[lane * NL + j] * d;
+      const float res = d / invd;
+      resid = fmaxf(resid, res * res);
+    }
+    for (int r = 0; r < nc; ++r) {  // contact normals
+      const int row = MAXNC + r;
+      const float invd = s.invd[row];
+      const float jd = warp_sum16(lane < 16 ? s.J[r][lane & 15] * dv : 0.f);
+      float d = s.rhs[row] - __shfl_sync(FULL, jd, 0) * invd;
+      const float old = s.lam[row];
+      const float sum = fmaxf(old + d, 0.f);
+      d = sum - old;
+      s.lam[row] = sum;
+      if (lane < 16) dv += s.W[r][lane] * d;
+      const float res = d / invd;
+      resid = fmaxf(resid, res * res);
+    }
+    for (int c = 0; c < nc; ++c) {  // friction cones
+      const int ra = nc + 2 * c, rb = ra + 1;
+      const int rowa = MAXNC + ra, rowb = MAXNC + rb;
+      const float lim = s.cmu[c] * s.lam[MAXNC + c];
+      const float ia = s.invd[rowa], ib = s.invd[rowb];
+      float ja = lane < 16 ? s.J[ra][lane & 15] * dv : 0.f;
+      float jb = lane < 16 ? s.J[rb][lane & 15] * dv : 0.f;
+      ja = __shfl_sync(FULL, warp_sum16(ja), 0);
+      jb = __shfl_sync(FULL, warp_sum16(jb), 0);
+      const float oa = s.lam[rowa], ob = s.lam[rowb];
+      float sa = oa + (s.rhs[rowa] - ja * ia), sb = ob + (s.rhs[rowb] - jb * ib);
+      const float nrm = sqrtf(sa * sa + sb * sb);
+      if (nrm > lim) {
+        const float sc = nrm > 0.f ? lim / nrm : 0.f;
+        sa *= sc; sb *= sc;
+      }
+      const float da = sa - oa, db = sb - ob;
+      s.lam[rowa] = sa; s.lam[rowb] = sb;
+      if (lane < 16) dv += s.W[ra][lane] * da + s.W[rb][lane] * db;
+      const float r1 = da / ia, r2 = db / ib;
+      resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
+    }
+    if (resid <= thresh) break;
+  }
+  __syncwarp();
+  // ---- integrate ----------------------------------------------------------------------------------------
+  const float unew = (lane < 16 ? s.u[lane & 15] : 0.f) + dv;
+  if (lane < NL) {
+    s.qd[lane] = unew;
+    s.q[lane] += dt * unew;
+  } else if (lane < 12) {
+    s.bv[lane - 9] = unew;
+    s.bp[lane - 9] += dt * unew;
+  } else if (lane < 15) {
+    s.bw[lane - 12] = unew;
+  }
+  __syncwarp();
+  if (lane == 0) {  // quaternion exponential map
+    const float wn = sqrtf(dot3(s.bw, s.bw)), th = wn * dt;
+    float ax[3];
+    if (wn < 1e-12f) { ax[0] = s.bw[0] * 0.5f * dt; ax[1] = s.bw[1] * 0.5f * dt; ax[2] = s.bw[2] * 0.5f * dt; }
+    else { const float sc = sinf(0.5f * th) / wn; ax[0] = s.bw[0] * sc; ax[1] = s.bw[1] * sc; ax[2] = s.bw[2] * sc; }
+    const float dq[4] = {ax[0], ax[1], ax[2], cosf(0.5f * th)}, q0[4] = {s.bq[0], s.bq[1], s.bq[2], s.bq[3]};
+    float r[4];
+    r[3] = dq[3] * q0[3] - dq[0] * q0[0] - dq[1] * q0[1] - dq[2] * q0[2];
+    r[0] = dq[3] * q0[0] + dq[0] * q0[3] + dq[1] * q0[2] - dq[2] * q0[1];
+    r[1] = dq[3] * q0[1] - dq[0] * q0[2] + dq[1] * q0[3] + dq[2] * q0[0];
+    r[2] = dq[3] * q0[2] + dq[0] * q0[1] - dq[1] * q0[0] + dq[2] * q0[3];
+    const float inv = rsqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+    s.bq[0] = r[0] * inv; s.bq[1] = r[1] * inv; s.bq[2] = r[2] * inv; s.bq[3] = r[3] * inv;
+  }
+  __syncwarp();
+}
+
+// ---- observation -------------------------------------------------------------------------------------------
+__device__ void observe(Smem& s, int lane, float* __restrict__ obs, float* __restrict__ ag) {
+  fk(s, s.q, lane);
+  if (lane == 0) {
+    float w[3] = {0, 0, 0}, vo[3] = {0, 0, 0};
+    int prev = -1;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      if (i == 7) continue;  // hand1 is not on the path to the EE
+      if (prev >= 0) {
+        float r[3] = {s.p[i][0] - s.p[prev][0], s.p[i][1] - s.p[prev][1], s.p[i][2] - s.p[prev][2]}, t[3];
+        cross3(t, w, r);
+        vo[0] += t[0]; vo[1] += t[1]; vo[2] += t[2];
+      }
+      w[0] += s.qd[i] * s.z[i][0]; w[1] += s.qd[i] * s.z[i][1]; w[2] += s.qd[i] * s.z[i][2];
+      prev = i;
+    }
+    float rc[3] = {s.c[EE][0] - s.p[EE][0], s.c[EE][1] - s.p[EE][1], s.c[EE][2] - s.p[EE][2]}, t[3];
+    cross3(t, w, rc);
+    const float* R = s.R[EE];
+    float eul[3];
+    const float sarg = -R[6];
+    if (sarg <= -0.99999f) { eul[0] = 0.f; eul[1] = -1.57079632679f; eul[2] = atan2f(-R[1], -R[2]); }
+    else if (sarg >= 0.99999f) { eul[0] = 0.f; eul[1] = 1.57079632679f; eul[2] = atan2f(-R[1], R[2]); }
+    else { eul[0] = atan2f(R[7], R[8]); eul[1] = asinf(sarg); eul[2] = atan2f(R[3], R[0]); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      obs[a] = s.p[EE][a];
+      obs[3 + a] = eul[a];
+      obs[6 + a] = vo[a] + t[a];   // link velocity reported at the COM
+      obs[9 + a] = w[a];
+      obs[12 + a] = s.bp[a];
+      obs[15 + a] = eul[a];        // reference bug kept: blockOrn slot repeats the gripper euler
+      obs[18 + a] = s.bp[a] - s.p[EE][a];
+      obs[21 + a] = s.bv[a];
+      obs[24 + a] = s.bw[a];
+      ag[a] = s.bp[a];
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void load_state(Smem& s, const float* __restrict__ st, int lane) {
+  for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {
+    const float v = st[i];
+    if (i < ST_QD) s.q[i - ST_Q] = v;
+    else if (i < ST_QT) s.qd[i - ST_QD] = v;
+    else if (i < ST_BPOS) s.qt[i - ST_QT] = v;
+    else if (i < ST_BQUAT) s.bp[i - ST_BPOS] = v;
+    else if (i < ST_BVEL) s.bq[i - ST_BQUAT] = v;
+    else if (i < ST_BANG) s.bv[i - ST_BVEL] = v;
+    else if (i < ST_GOAL) s.bw[i - ST_BANG] = v;
+    else if (i < ST_PAD) s.goal[i - ST_GOAL] = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void store_state(const Smem& s, float* __restrict__ st, int lane) {
+  for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {
+    float v = 0.f;
+    if (i < ST_QD) v = s.q[i - ST_Q];
+    else if (i < ST_QT) v = s.qd[i - ST_QD];
+    else if (i < ST_BPOS) v = s.qt[i - ST_QT];
+    else if (i < ST_BQUAT) v = s.bp[i - ST_BPOS];
+    else if (i < ST_BVEL) v = s.bq[i - ST_BQUAT];
+    else if (i < ST_BANG) v = s.bv[i - ST_BVEL];
+    else if (i < ST_GOAL) v = s.bw[i - ST_BANG];
+    else if (i < ST_PAD) v = s.goal[i - ST_GOAL];
+    st[i] = v;
+  }
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) env_step_kernel(const float* __restrict__ model_g, EnvParams ep,
+                                                      float* __restrict__ state, const float* __restrict__ actions,
+                                                      float* __restrict__ obs, float* __restrict__ ag,
+                                                      float* __restrict__ reward, float* __restrict__ success) {
+  __shared__ Smem s;
+  const int e = blockIdx.x, lane = threadIdx.x;
+  stage_model(s, model_g, lane);
+  load_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = fminf(fmaxf(actions[e * 4 + i], -0.5f), 0.5f);
+  if (ep.task == BMI_TASK_PUSH) a[3] = 0.f;  // bmirobot_env_push_F.py:94
+  fk(s, s.q, lane);
+  if (ep.task == BMI_TASK_PICK) {  // auto-grip (bmirobot_env_pickandplace_v2.py:94-95)
+    find_contacts(s, ep, model_g, 1e-4f, lane);
+    bool touch = false;
+    for (int c = 0; c < s.nc; ++c) touch |= (s.chasb[c] && s.clink[c] >= 0 && s.cdist[c] < 1e-4f);
+    if (touch) a[3] = -1.f;
+  }
+  // applyAction (bmirobot.py:129-162)
+  float target[3] = {fminf(fmaxf(s.p[EE][0] + a[0], -1.f), 1.f), fminf(fmaxf(s.p[EE][1] + a[1], -1.f), 1.f),
+                     fminf(fmaxf(s.p[EE][2] + a[2], 0.f), 1.f)};
+  __syncwarp();
+  solve_ik(s, target, lane);
+  if (lane < 7) s.qt[lane] = s.qik[lane];
+  else if (lane == 7) s.qt[7] = s.q[7] + a[3];  // sent_hand_moving (bmirobot.py:163-191)
+  else if (lane == 8) s.qt[8] = s.q[8] - a[3];
+  __syncwarp();
+  const int nsub = (int)P(s, MP_N_SUBSTEPS);
+  for (int i = 0; i < nsub; ++i) substep(s, ep, model_g, lane);
+  observe(s, lane, obs + (size_t)e * BMI_OBS_DIM, ag + (size_t)e * BMI_GOAL_DIM);
+  if (lane == 0) {
+    const float dx = s.bp[0] - s.goal[0], dy = s.bp[1] - s.goal[1], dz = s.bp[2] - s.goal[2];
+    const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float thr = P(s, MP_DIST_THRESHOLD);
+    if (success) success[e] = dist < thr ? 1.f : 0.f;
+    if (reward) reward[e] = dist > thr ? -1.f : -0.f;
+  }
+  store_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
+}
+
+__global__ void __launch_bounds__(32) env_reset_kernel(const float* __restrict__ model_g, float* __restrict__ state,
+                                                       const unsigned char* __restrict__ mask,
+                                                       const float* __restrict__ init, float* __restrict__ obs,
+                                                       float* __restrict__ ag, float* __restrict__ g) {
+  __shared__ Smem s;
+  const int e = blockIdx.x, lane = threadIdx.x;
+  stage_model(s, model_g, lane);
+  float* st = state + (size_t)e * BMI_ENV_STATE_DIM;
+  if (mask == nullptr || mask[e]) {
+    const float* in = init + (size_t)e * 8;
+    for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {
+      float v = 0.f;
+      if (i >= ST_BPOS && i < ST_BPOS + 3) v = in[i - ST_BPOS];
+      else if (i == ST_BQUAT + 2) v = sinf(0.5f * in[3]);
+      else if (i == ST_BQUAT + 3) v = cosf(0.5f * in[3]);
+      else if (i >= ST_GOAL && i < ST_GOAL + 3) v = in[4 + i - ST_GOAL];
+      st[i] = v;
+    }
+    __syncwarp();
+  }
+  load_state(s, st, lane);
+  observe(s, lane, obs + (size_t)e * BMI_OBS_DIM, ag + (size_t)e * BMI_GOAL_DIM);
+  if (lane < 3) g[e * 3 + lane] = s.goal[lane];
+}
+
+// rejection-sampled block / goal placement (bmirobot_env_push_F.py:117-132; pick: pickandplace_v2.py:116-131)
+__global__ void env_sample_init_kernel(int n, int task, uint64_t seed, const uint64_t* __restrict__ counter,
+                                       float* __restrict__ init) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint64_t c = *counter + (uint64_t)e;
+  float x = 0, y = 0, ang = 0, xt = 0, yt = 0, zt = 0.2f;
+  for (int attempt = 0; attempt < 100; ++attempt) {
+    Philox4 p0 = philox4x32_10(seed, c * 128 + 2 * attempt, kStreamReset);
+    Philox4 p1 = philox4x32_10(seed, c * 128 + 2 * attempt + 1, kStreamReset);
+    x = 0.15f + 0.2f * u24(p0.v[0]);
+    y = u24(p0.v[1]) * 0.3f + 0.2f;
+    ang = 3.14f * 0.5f + 3.1415925438f * u24(p0.v[2]);
+    xt = 0.35f * u24(p0.v[3]);
+    if (task == BMI_TASK_PUSH) { yt = u24(p1.v[0]) * 0.3f + 0.2f; zt = 0.2f; }
+    else { yt = u24(p1.v[0]) * 0.25f + 0.3f; zt = 0.3f + 0.2f * u24(p1.v[1]); }
+    const float dx = x - xt, dy = y - yt, dz = 0.2f - zt;
+    if (sqrtf(dx * dx + dy * dy + dz * dz) >= 0.15f) break;
+  }
+  float* o = init + (size_t)e * 8;
+  o[0] = x; o[1] = y; o[2] = 0.2f; o[3] = ang; o[4] = xt; o[5] = yt; o[6] = zt; o[7] = 0.f;
+}
+__global__ void advance_counter_kernel3(uint64_t* counter, uint64_t by) { *counter += by; }
+
+__global__ void copy_state_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+}  // namespace bmi
+
+using namespace bmi;
+
+struct bmi_env {
+  int n_envs = 0;
+  EnvParams ep;
+  float* model_dev = nullptr;
+  float* state_dev = nullptr;
+  int64_t model_floats = 0;
+};
+
+extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const void* blob, int64_t bytes) {
+  BMI_REQUIRE(out && blob, "bmi_env_create: null pointer");
+  BMI_REQUIRE(n_envs > 0, "bmi_env_create: n_envs must be positive");
+  BMI_REQUIRE(task == BMI_TASK_PUSH || task == BMI_TASK_PICK, "bmi_env_create: unknown task %d", task);
+  BMI_REQUIRE(bytes >= (int64_t)(BMI_MODEL_HDR * sizeof(float)) && bytes % 4 == 0, "bmi_env_create: bad model blob size");
+  const float* b = (const float*)blob;
+  const int64_t n = bytes / 4;
+  BMI_REQUIRE(b[MP_MAGIC] == BMI_MODEL_MAGIC && (int64_t)b[MP_TOTAL] == n && n <= BMI_MODEL_MAX_FLOATS,
+              "bmi_env_create: model blob magic/size mismatch");
+  BMI_REQUIRE((int)b[MP_N_LINKS] == NL && (int)b[MP_EE_LINK] == EE && (int)b[MP_N_SHAPES] <= BMI_MAX_SHAPES &&
+                  (int)b[MP_LINKS_OFF] == BMI_MODEL_HDR,
+              "bmi_env_create: model does not match the compiled arm topology");
+  for (int i = 0; i < NL; ++i) {
+    const float* lk = b + BMI_MODEL_HDR + i * BMI_LINK_STRIDE;
+    BMI_REQUIRE((int)lk[ML_PARENT] == parent_of(i), "bmi_env_create: link %d has parent %d, kernel expects %d", i,
+                (int)lk[ML_PARENT], parent_of(i));
+  }
+  for (int si = 0; si < (int)b[MP_N_SHAPES]; ++si) {
+    const float* sh = b + (int)b[MP_SHAPES_OFF] + si * BMI_SHAPE_STRIDE;
+    BMI_REQUIRE((int)sh[MS_NVERTS] <= 24 && ((int)b[MP_POOL_OFF] + (int)sh[MS_PLANE_OFF]) % 4 == 0,
+                "bmi_env_create: shape %d needs <= 24 vertices and 16-byte aligned planes", si);
+  }
+  bmi_env* h = new bmi_env();
+  h->n_envs = n_envs;
+  h->ep.task = task;
+  const int o = task == BMI_TASK_PUSH ? MP_PUSH_HX : MP_PICK_HX;
+  for (int a = 0; a < 3; ++a) h->ep.bh[a] = b[o + a];
+  h->ep.bmass = b[o + 3];
+  h->ep.bmu = b[o + 4];
+  const float lx = 2 * h->ep.bh[0], ly = 2 * h->ep.bh[1], lz = 2 * h->ep.bh[2], mm = h->ep.bmass / 12.f;
+  h->ep.binertia[0] = mm * (ly * ly + lz * lz);
+  h->ep.binertia[1] = mm * (lx * lx + lz * lz);
+  h->ep.binertia[2] = mm * (lx * lx + ly * ly);
+  h->model_floats = n;
+  if (cudaMalloc(&h->model_dev, n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&h->state_dev, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)) != cudaSuccess) {
+    set_error("bmi_env_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    bmi_env_destroy(h);
+    return BMI_ERR_CUDA;
+  }
+  BMI_CUDA_CHECK(cudaMemcpy(h->model_dev, blob, n * sizeof(float), cudaMemcpyHostToDevice));
+  BMI_CUDA_CHECK(cudaMemset(h->state_dev, 0, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)));
+  *out = h;
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_destroy(bmi_env* h) {
+  if (!h) return BMI_OK;
+  if (h->model_dev) cudaFree(h->model_dev);
+  if (h->state_dev) cudaFree(h->state_dev);
+  delete h;
+  return BMI_OK;
+}
+
+extern "C" int32_t bmi_env_num_envs(const bmi_env* h) { return h ? h->n_envs : -1; }
+
+extern "C" int bmi_env_reset(bmi_env* h, const uint8_t* mask, const float* init, float* obs, float* ag, float* g,
+                             bmi_stream_t stream) {
+  BMI_REQUIRE(h && init && obs && ag && g, "bmi_env_reset: null pointer");
+  env_reset_kernel<<<h->n_envs, 32, 0, as_stream(stream)>>>(h->model_dev, h->state_dev, mask, init, obs, ag, g);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_sample_init(bmi_env* h, uint64_t seed, uint64_t* counter, float* init, bmi_stream_t stream) {
+  BMI_REQUIRE(h && counter && init, "bmi_env_sample_init: null pointer");
+  env_sample_init_kernel<<<(h->n_envs + 127) / 128, 128, 0, as_stream(stream)>>>(h->n_envs, h->ep.task, seed, counter, init);
+  BMI_LAUNCHED();
+  advance_counter_kernel3<<<1, 1, 0, as_stream(stream)>>>(counter, (uint64_t)h->n_envs);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_step(bmi_env* h, const float* actions, float* obs, float* ag, float* reward, float* success,
+                            bmi_stream_t stream) {
+  BMI_REQUIRE(h && actions && obs && ag, "bmi_env_step: null pointer");
+  env_step_kernel<<<h->n_envs, 32, 0, as_stream(stream)>>>(h->model_dev, h->ep, h->state_dev, actions, obs, ag, reward, success);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_get_state(bmi_env* h, float* st, bmi_stream_t stream) {
+  BMI_REQUIRE(h && st, "bmi_env_get_state: null pointer");
+  const int n = h->n_envs * BMI_ENV_STATE_DIM;
+  copy_state_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(st, h->state_dev, n);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_set_state(bmi_env* h, const float* st, bmi_stream_t stream) {
+  BMI_REQUIRE(h && st, "bmi_env_set_state: null pointer");
+  const int n = h->n_envs * BMI_ENV_STATE_DIM;
+  copy_state_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(h->state_dev, st, n);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}

@@ -67,13 +67,13 @@ class normalizer:
             a = a.astype(np.float64)
         return torch.as_tensor(np.ascontiguousarray(a)).to(self.device), True
 
-    def update(self, v):
-        """normalizer.py:25-31."""
+    def update(self, v, pre_clip=0.0):
+        """normalizer.py:25-31.  pre_clip > 0 fuses ddpg_agent._preproc_og's clip into the kernel."""
         t, _ = self._as_dev(v)
         t = t.reshape(-1, self.size)
         with self.lock:
             _lib.call("bmi_norm_update", _lib.ptr(t), int(t.shape[0]), int(self.size), _lib.dtype_code(t.dtype),
-                      _lib.ptr(self.local_sum_dev), _lib.ptr(self.local_sumsq_dev), _lib.ptr(self.local_count_dev),
+                      float(pre_clip), _lib.ptr(self.local_sum_dev), _lib.ptr(self.local_sumsq_dev), _lib.ptr(self.local_count_dev),
                       _lib.stream_ptr())
 
     def sync(self, local_sum, local_sumsq, local_count):

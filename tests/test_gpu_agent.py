@@ -1,0 +1,97 @@
+"""GPU end-to-end: one vectorised training cycle through the reference-shaped agent API."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _agent(tmp_path, n_envs=32, **kw):
+    from rl_arm_under_sparse_reward_b200.arguments import Args
+    from rl_arm_under_sparse_reward_b200.bmirobot_env.vec_env import BmiVecEnv
+    from rl_arm_under_sparse_reward_b200.ddpg_agent import ddpg_agent
+    from rl_arm_under_sparse_reward_b200.train import get_env_params
+    a = Args()
+    a.add_demo, a.n_envs, a.verbose, a.buffer_size, a.save_dir = False, n_envs, False, 256 * 100, str(tmp_path) + "/"
+    for k, v in kw.items():
+        setattr(a, k, v)
+    env = BmiVecEnv(n_envs, task=a.train_type, seed=a.seed)
+    torch.manual_seed(a.seed)
+    return ddpg_agent(a, env, get_env_params(env)), a
+
+
+def test_one_cycle_graphed_equals_eager(tmp_path):
+    ag1, _ = _agent(tmp_path, use_cuda_graphs=True)
+    ag2, _ = _agent(tmp_path, use_cuda_graphs=False)
+    ag2.actor_network.flat.copy_(ag1.actor_network.flat)
+    ag2.critic_network.flat.copy_(ag1.critic_network.flat)
+    ag2.actor_target_network.flat.copy_(ag1.actor_target_network.flat)
+    ag2.critic_target_network.flat.copy_(ag1.critic_target_network.flat)
+    for ag in (ag1, ag2):
+        for _ in range(2):      # second call replays the captured graph
+            ag.rollout(0)
+            ag.buffer.store_episode([ag.ep['obs'], ag.ep['ag'], ag.ep['g'], ag.ep['actions']])
+            ag._update_normalizer()
+            ag.update_many(4)
+            ag._soft_update_target_network()
+    torch.cuda.synchronize()
+    assert torch.equal(ag1.ep['obs'], ag2.ep['obs']) and torch.equal(ag1.ep['actions'], ag2.ep['actions'])
+    assert torch.equal(ag1.actor_network.flat, ag2.actor_network.flat)
+    assert torch.equal(ag1.critic_target_network.flat, ag2.critic_target_network.flat)
+    assert ag1.buffer.current_size == 64 and ag1.env_steps == 2 * 32 * 100 and ag1.updates == 8
+    # episode arrays are self-consistent: ag == obs[12:15], g constant per episode
+    ep = ag1.ep
+    assert torch.equal(ep['ag'], ep['obs'][:, :, 12:15])
+    assert torch.equal(ep['g'], ep['g'][:, :1].expand_as(ep['g']))
+    assert ep['actions'].abs().max() <= 0.5
+
+
+def test_numpy_stream_update_is_bit_reproducible_and_matches_oracle_sampling(tmp_path):
+    from oracle import learner_oracle as lo
+    ag, a = _agent(tmp_path, device_rng=False, buffer_dtype="float64")
+    ag.rollout(0)
+    ag.buffer.store_episode([ag.ep['obs'], ag.ep['ag'], ag.ep['g'], ag.ep['actions']])
+    np.random.seed(4)
+    ag._update_normalizer()
+    ag._update_network()
+    torch.cuda.synchronize()
+    x_gpu = ag._x.cpu().numpy().copy()
+    # replay the same numpy stream through the oracle
+    np.random.seed(4)
+    bufs = {k: v[:32].cpu().numpy() for k, v in ag.buffer.buffers.items()}
+    new = {k: ag.ep[k].double().cpu().numpy() for k in ('obs', 'ag', 'g', 'actions')}
+    on, gn = lo.Normalizer(27, clip=5), lo.Normalizer(3, clip=5)
+    tr = lo.her_sample_with_draws(new, lo.her_draw_numpy(32, 100, 100 * 16), 0.8)
+    on.update(np.clip(tr['obs'], -200, 200))
+    gn.update(np.clip(tr['g'], -200, 200))
+    on.recompute_stats()
+    gn.recompute_stats()
+    assert np.array_equal(ag.o_norm.mean, on.mean) and np.array_equal(ag.o_norm.std, on.std)
+    x, xn, act, r = lo.network_inputs(lo.her_sample_with_draws(bufs, lo.her_draw_numpy(32, 100, 256), 0.8), on, gn)
+    assert np.array_equal(x_gpu, x) and np.array_equal(ag._r.cpu().numpy(), r[:, 0])
+
+
+def test_eval_and_checkpoint_format(tmp_path):
+    ag, a = _agent(tmp_path, n_envs=8, n_test_rollouts=8)
+    rate = ag._eval_agent()
+    assert 0.0 <= rate <= 1.0
+    path = ag.save_checkpoint()
+    o_mean, o_std, g_mean, g_std, sd = torch.load(path, weights_only=False)
+    assert o_mean.shape == (27,) and g_std.shape == (3,) and o_mean.dtype == np.float32
+    assert list(sd.keys()) == ['fc1.weight', 'fc1.bias', 'fc2.weight', 'fc2.bias', 'fc3.weight', 'fc3.bias',
+                               'action_out.weight', 'action_out.bias']
+    assert sd['fc1.weight'].shape == (256, 30) and not sd['fc1.weight'].is_cuda
+    # the reference's own actor class shape (models.py:11-26) loads it
+    from oracle.ddpg_oracle import Actor
+    Actor().load_state_dict(sd)
+
+
+def test_demo_buffer_preload(tmp_path, golden_dir):
+    demo = os.path.join(golden_dir, "demo_small.npz")
+    ag, a = _agent(tmp_path, n_envs=4, add_demo=True, demo_name=demo)
+    d = np.load(demo)
+    assert ag.buffer.current_size == d["obs"].shape[0]
+    assert np.allclose(ag.buffer.buffers['obs'][:2].cpu().numpy(), d["obs"][:2].astype(np.float32))
+    assert float(ag.o_norm.total_count[0]) == 1.0     # normalisers are NOT updated from demos (ddpg_agent.py:49-53)

@@ -1,0 +1,216 @@
+"""Bake the bmirobot model blob consumed by the physics kernel and by the C oracle.
+
+Reads the reference's URDF + STL meshes (read-only, build container only) and writes
+    rl_arm_under_sparse_reward_b200/assets/bmirobot_model.bin   (float32 little-endian)
+    rl_arm_under_sparse_reward_b200/assets/bmirobot_model.json  (same numbers, readable)
+Only DERIVED model constants are stored (kinematic tree of the right arm, inertial
+parameters, simplified convex collision polytopes, world/solver constants); no reference
+source is copied.  Layout = the MODEL_* offsets below, mirrored in csrc/physics_model.h.
+
+Facts restated from the reference (paths relative to the reference tree):
+  URDF_model/bmirobot_description/urdf/robotarm_description.urdf:186-207  base chain
+  ... :423-501   right_joint1..7, right_hand_joint1/2 origins, axes, limits, damping 0.7
+  ... :222-226   every link: mass 1, inertial origin (0,0,1)
+  bmirobot_env/bmirobot.py:58-61   flags=9 (self-collision, inertia NOT from file), base pose
+  bmirobot_env/bmirobot.py:77      table at (0,0.3,-0.45)  => table top z = 0.175
+  URDF_model/cube_small_push.urdf / cube_small_pick.urdf   box sizes and masses
+  bmirobot_env/bmirobot_env_push_F.py:111-115,161   150 solver iterations, dt 1/240, g=-10
+"""
+import json
+import os
+import struct
+import sys
+import xml.etree.ElementTree as ET
+
+import numpy as np
+from scipy.spatial import ConvexHull
+
+REF = "/root/reference"
+URDF = os.path.join(REF, "URDF_model/bmirobot_description/urdf/robotarm_description.urdf")
+MESH_DIR = os.path.join(REF, "URDF_model/bmirobot_description/modle/stl_V5")
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "rl_arm_under_sparse_reward_b200", "assets")
+
+# ---- blob layout (float32 indices) ---------------------------------------------------------
+MAGIC = 20251017.0
+HDR = 64            # header + params
+LINK_STRIDE = 32
+MAX_LINKS = 9
+SHAPE_STRIDE = 12   # link, n_verts, n_planes, vert_off, plane_off, sphere c(3), sphere r, mu, pad2
+P = dict(magic=0, version=1, n_links=2, n_shapes=3, links_off=4, shapes_off=5, pool_off=6, total=7,
+         dt=8, gravity=9, n_substeps=10, solver_iters=11, residual_thresh=12, erp_joint=13, erp_contact=14,
+         linear_slop=15, motor_kp=16, motor_kd=17, motor_force=18, lin_damp=19, ang_damp=20,
+         ik_damping=21, ik_iters=22, ik_thresh=23, ik_max_angle=24, table_z=25, mu_table=26,
+         contact_margin=27, base_px=28, base_py=29, base_pz=30, ee_link=31,
+         push_hx=32, push_hy=33, push_hz=34, push_mass=35, push_mu=36,
+         pick_hx=37, pick_hy=38, pick_hz=39, pick_mass=40, pick_mu=41,
+         dist_threshold=42, joint_limit_force=43, block_margin=44, table_margin=45, ik_pos_at_com=46,
+         self_collision=47)
+L = dict(parent=0, jpos=1, jrot=4, axis=13, lo=16, hi=17, damping=18, mass=19, com=20, inertia=23, shape=26, mu=27)
+
+
+def rpy_to_mat(r, p, y):
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def load_stl(fn):
+    b = open(fn, "rb").read()
+    n = struct.unpack("<I", b[80:84])[0]
+    assert 84 + n * 50 == len(b), "binary STL expected"
+    a = np.frombuffer(b[84:], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+    return np.unique(a["v"].reshape(-1, 3).astype(np.float64), axis=0)
+
+
+def simplify_hull(v, k):
+    """greedy inner approximation: k hull vertices, each the farthest outside the current hull"""
+    h = ConvexHull(v)
+    hv = v[h.vertices]
+    idx = set()
+    for a in range(3):
+        idx.add(int(hv[:, a].argmin()))
+        idx.add(int(hv[:, a].argmax()))
+    idx = sorted(idx)
+    while len(idx) < k:
+        cur = ConvexHull(hv[idx])
+        d = (hv @ cur.equations[:, :3].T + cur.equations[:, 3]).max(1)
+        j = int(d.argmax())
+        if d[j] < 1e-9:
+            break
+        idx.append(j)
+    s = hv[idx]
+    hs = ConvexHull(s)
+    eq = hs.equations
+    # merge coplanar facets
+    keep = []
+    for e in eq:
+        if not any(np.allclose(e, f, atol=1e-7) for f in keep):
+            keep.append(e)
+    return s[hs.vertices] if len(hs.vertices) == len(s) else s, np.array(keep), hs.volume / h.volume
+
+
+def main(k_verts=24):
+    root = ET.parse(URDF).getroot()
+    joints = {j.get("name"): j for j in root.findall("joint")}
+    links = {l.get("name"): l for l in root.findall("link")}
+
+    def jinfo(name):
+        j = joints[name]
+        o = j.find("origin")
+        xyz = [float(x) for x in (o.get("xyz") if o is not None else "0 0 0").split()]
+        rpy = [float(x) for x in (o.get("rpy") if o is not None and o.get("rpy") else "0 0 0").split()]
+        ax = j.find("axis")
+        axis = [float(x) for x in ax.get("xyz").split()] if ax is not None else [0, 0, 0]
+        lim = j.find("limit")
+        dyn = j.find("dynamics")
+        return dict(xyz=xyz, rpy=rpy, axis=axis, parent=j.find("parent").get("link"), child=j.find("child").get("link"),
+                    lo=float(lim.get("lower")) if lim is not None else 0.0, hi=float(lim.get("upper")) if lim is not None else 0.0,
+                    damping=float(dyn.get("damping")) if dyn is not None else 0.0)
+
+    chain = ["right_joint1", "right_joint2", "right_joint3", "right_joint4", "right_joint5", "right_joint6",
+             "right_joint7", "right_hand_joint1", "right_hand_joint2"]
+    link_index = {}
+    # base: world -> odom_combined -> base_link (+0.45 z) -> right_link1 (+0.22 x); robot base at (-0.1, 0, 0.07)
+    base = np.array([-0.1, 0.0, 0.07])
+    for jn in ("fixed", "virtual_joint", "rightvirtual_joint"):
+        ji = jinfo(jn)
+        assert ji["rpy"] == [0, 0, 0]
+        base = base + np.array(ji["xyz"])
+    link_index["right_link1"] = -1
+
+    mesh_of = {}
+    for ln, l in links.items():
+        c = l.find("collision")
+        if c is not None and c.find("geometry/mesh") is not None:
+            mesh_of[ln] = os.path.basename(c.find("geometry/mesh").get("filename")).replace(".dae", ".STL")
+
+    blob_links = np.zeros((MAX_LINKS, LINK_STRIDE), np.float64)
+    link_names = []
+    for i, jn in enumerate(chain):
+        ji = jinfo(jn)
+        ln = ji["child"]
+        link_index[ln] = i
+        link_names.append(ln)
+        row = blob_links[i]
+        row[L["parent"]] = link_index[ji["parent"]]
+        row[L["jpos"]:L["jpos"] + 3] = ji["xyz"]
+        row[L["jrot"]:L["jrot"] + 9] = rpy_to_mat(*ji["rpy"]).reshape(-1)
+        row[L["axis"]:L["axis"] + 3] = ji["axis"]
+        row[L["lo"]], row[L["hi"]], row[L["damping"]] = ji["lo"], ji["hi"], ji["damping"]
+        inert = links[ln].find("inertial")
+        row[L["mass"]] = float(inert.find("mass").get("value"))
+        com = np.array([float(x) for x in inert.find("origin").get("xyz").split()])
+        row[L["com"]:L["com"] + 3] = com
+        # flags=9 lacks URDF_USE_INERTIA_FROM_FILE: Bullet recomputes the diagonal inertia from the
+        # AABB of the collision shape expressed in the inertial frame (btCompoundShape box formula);
+        # convex hull margin 1 mm on each side
+        v = load_stl(os.path.join(MESH_DIR, mesh_of[ln]))
+        ext = (v.max(0) - v.min(0)) + 2 * 0.001
+        m = row[L["mass"]]
+        row[L["inertia"]:L["inertia"] + 3] = m / 12.0 * np.array([ext[1] ** 2 + ext[2] ** 2, ext[0] ** 2 + ext[2] ** 2,
+                                                                  ext[0] ** 2 + ext[1] ** 2])
+        row[L["shape"]] = -1
+        fr = links[ln].find("contact/lateral_friction")
+        row[L["mu"]] = float(fr.get("value")) if fr is not None else 0.5
+
+    # collision polytopes for the links that can reach the block / the table
+    coll_links = ["right_link6", "right_link8", "right_hand1", "right_hand2"]
+    shapes, pool = [], []
+    info = {}
+    for ln in coll_links:
+        v = load_stl(os.path.join(MESH_DIR, mesh_of[ln]))
+        sv, planes, ratio = simplify_hull(v, k_verts)
+        c = 0.5 * (sv.max(0) + sv.min(0))
+        r = np.linalg.norm(sv - c, axis=1).max()
+        li = link_index[ln]
+        blob_links[li][L["shape"]] = len(shapes)
+        vert_off = len(pool)
+        pool.extend(sv.reshape(-1).tolist())
+        plane_off = len(pool)
+        pool.extend(planes.reshape(-1).tolist())
+        shapes.append([li, len(sv), len(planes), vert_off, plane_off, c[0], c[1], c[2], r, blob_links[li][L["mu"]], 0, 0])
+        info[ln] = dict(verts=len(sv), planes=len(planes), volume_ratio=round(float(ratio), 4))
+
+    hdr = np.zeros(HDR, np.float64)
+    hdr[P["magic"]], hdr[P["version"]] = MAGIC, 1
+    hdr[P["n_links"]], hdr[P["n_shapes"]] = len(chain), len(shapes)
+    hdr[P["links_off"]] = HDR
+    hdr[P["shapes_off"]] = HDR + MAX_LINKS * LINK_STRIDE
+    hdr[P["pool_off"]] = hdr[P["shapes_off"]] + len(shapes) * SHAPE_STRIDE
+    hdr[P["total"]] = hdr[P["pool_off"]] + len(pool)
+    hdr[P["dt"]], hdr[P["gravity"]], hdr[P["n_substeps"]] = 1.0 / 240.0, -10.0, 20
+    hdr[P["solver_iters"]], hdr[P["residual_thresh"]] = 150, 1e-7
+    hdr[P["erp_joint"]], hdr[P["erp_contact"]], hdr[P["linear_slop"]] = 0.2, 0.08, 1e-5
+    hdr[P["motor_kp"]], hdr[P["motor_kd"]], hdr[P["motor_force"]] = 0.03, 1.0, 500.0
+    hdr[P["lin_damp"]], hdr[P["ang_damp"]] = 0.04, 0.04
+    hdr[P["ik_damping"]], hdr[P["ik_iters"]], hdr[P["ik_thresh"]], hdr[P["ik_max_angle"]] = 0.1, 20, 1e-4, np.pi / 4
+    hdr[P["table_z"]], hdr[P["mu_table"]] = 0.175, 1.0
+    hdr[P["contact_margin"]] = 0.002
+    hdr[P["base_px"]:P["base_px"] + 3] = base
+    hdr[P["ee_link"]] = link_index["right_hand2"]
+    hdr[P["push_hx"]:P["push_hx"] + 3] = [0.02, 0.02, 0.02]
+    hdr[P["push_mass"]], hdr[P["push_mu"]] = 1.0, 0.5
+    hdr[P["pick_hx"]:P["pick_hx"] + 3] = [0.02, 0.02, 0.04]
+    hdr[P["pick_mass"]], hdr[P["pick_mu"]] = 2.0, 0.5
+    hdr[P["dist_threshold"]] = 0.05
+    hdr[P["joint_limit_force"]] = 1000.0
+    hdr[P["block_margin"]], hdr[P["table_margin"]] = 0.002, 0.0
+    hdr[P["ik_pos_at_com"]] = 0.0
+    hdr[P["self_collision"]] = 0.0
+
+    blob = np.concatenate([hdr, blob_links.reshape(-1), np.array(shapes, np.float64).reshape(-1), np.array(pool)])
+    assert blob.shape[0] == int(hdr[P["total"]])
+    os.makedirs(OUT_DIR, exist_ok=True)
+    blob.astype("<f4").tofile(os.path.join(OUT_DIR, "bmirobot_model.bin"))
+    with open(os.path.join(OUT_DIR, "bmirobot_model.json"), "w") as f:
+        json.dump(dict(layout=dict(HDR=HDR, LINK_STRIDE=LINK_STRIDE, MAX_LINKS=MAX_LINKS, SHAPE_STRIDE=SHAPE_STRIDE, P=P, L=L),
+                       links=link_names, base=base.tolist(), shapes=info, n_floats=int(blob.shape[0])), f, indent=1)
+    print("links", link_names)
+    print("base", base, "shapes", info, "floats", blob.shape[0])
+
+
+if __name__ == "__main__":
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 24)
