@@ -52,7 +52,7 @@ struct __align__(16) Smem {
   int nc;
   // rows
   float J[3 * MAXC][16], W[3 * MAXC][16];
-  float invd[MAXR], rhs[MAXR], lo[MAXR], hi[MAXR], lam[MAXR];
+  float invd[MAXR], diag[MAXR], rhs[MAXR], lo[MAXR], hi[MAXR], lam[MAXR];
   int ncj[MAXNC];                 // joint index (+1, sign = direction) of each non-contact row
   // IK scratch
   float A[NL * NL], b[NL], qik[NL];
@@ -168,9 +168,9 @@ __device__ void fk(Smem& s, const float* q, int lane) {
 // ---- recursive Newton-Euler, one independent sweep per lane ------------------------------------
 // tau_j = z_j . sum_{k in subtree(j)} [ N_k + (c_k - p_j) x F_k ]   (accumulated pairwise so that no
 // per-link force arrays are needed; the tree topology is a compile-time constant).
-template <bool kBias>
-__device__ __forceinline__ void rnea_lane(const Smem& s, const float* qd, int unit, float gz, float kl, float ka,
+__device__ __forceinline__ void rnea_lane(const Smem& s, bool is_bias, int unit, float gz, float kl, float ka,
                                           float* tau) {
+  constexpr bool kBias = true;  // the velocity terms are evaluated by every sweep (zeros for the unit sweeps)
   float w[3] = {0, 0, 0}, al[3] = {0, 0, 0}, a[3] = {0, 0, -gz}, vo[3] = {0, 0, 0};
   float w6[3], al6[3], a6[3], vo6[3];
 #pragma unroll
@@ -190,8 +190,8 @@ __device__ __forceinline__ void rnea_lane(const Smem& s, const float* qd, int un
       a[0] += t[0]; a[1] += t[1]; a[2] += t[2];
       if (kBias) { cross3(t, w, r); cross3(t2, w, t); a[0] += t2[0]; a[1] += t2[1]; a[2] += t2[2]; }
     }
-    const float qdi = kBias ? qd[i] : 0.f;
-    const float qddi = (!kBias && unit == i) ? 1.f : 0.f;
+    const float qdi = is_bias ? s.qd[i] : 0.f;
+    const float qddi = (!is_bias && unit == i) ? 1.f : 0.f;
     const float* zi = s.z[i];
     if (kBias) { cross3(t, w, zi); al[0] += qdi * t[0]; al[1] += qdi * t[1]; al[2] += qdi * t[2]; }
     al[0] += qddi * zi[0]; al[1] += qddi * zi[1]; al[2] += qddi * zi[2];
@@ -486,14 +486,14 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   fk(s, s.q, lane);
   {  // mass matrix columns (lanes 0..8) and bias (lane 9)
     float tau[NL];
-    if (lane < NL) {
-      rnea_lane<false>(s, nullptr, lane, 0.f, 0.f, 0.f, tau);
+    if (lane <= NL) {  // one code path for all ten sweeps (no divergence): unit lanes see zero velocity / gravity
+      const bool is_bias = lane == NL;
+      rnea_lane(s, is_bias, lane, is_bias ? gz : 0.f, is_bias ? kl : 0.f, is_bias ? ka : 0.f, tau);
 #pragma unroll
-      for (int i = 0; i < NL; ++i) s.L[i * NL + lane] = tau[i];
-    } else if (lane == 9) {
-      rnea_lane<true>(s, s.qd, -1, gz, kl, ka, tau);
-#pragma unroll
-      for (int i = 0; i < NL; ++i) s.bias[i] = tau[i];
+      for (int i = 0; i < NL; ++i) {
+        if (is_bias) s.bias[i] = tau[i];
+        else s.L[i * NL + lane] = tau[i];
+      }
     }
   }
   __syncwarp();
@@ -628,7 +628,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
       for (int a = 0; a < NU; ++a) { s.J[ri][a] = J[a]; s.W[ri][a] = Wv[a]; }
       s.J[ri][15] = 0.f; s.W[ri][15] = 0.f;
       const int row = MAXNC + ri;
-      s.invd[row] = invd; s.lam[row] = 0.f;
+      s.invd[row] = invd; s.diag[row] = diag; s.lam[row] = 0.f;
       if (kind == 0) {
         const float pen = s.cdist[ci] + P(s, MP_LINEAR_SLOP);
         float pos_err = 0.f, vel_err = -rel;
@@ -643,12 +643,38 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   }
   __syncwarp();
   // ---- projected Gauss-Seidel; lane d holds dv[d] -------------------------------------------------------
+  // Motor rows (always 9, J = e_j) live entirely in registers: lane j owns row j's rhs / 1/diag / lambda and
+  // every lane < 9 keeps its row of M^-1 (mrow[j] = Minv[lane][j]); one shuffle broadcasts dv[j].
   float dv = 0.f;
+  float mrow[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) mrow[j] = lane < NL ? s.Minv[lane * NL + j] : 0.f;
+  const int ml = lane < NL ? lane : 0;
+  const float m_invd = s.invd[ml], m_diag = s.Minv[ml * NL + ml], m_rhs = s.rhs[ml];
+  float m_lam = 0.f;
+  float mdiag[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) mdiag[j] = __shfl_sync(FULL, m_diag, j);
+  // lanes 0..15 use both halves of the warp for contact rows: the 16-lane butterfly already leaves the dot
+  // product in every lane of the lower half; the upper half holds zeros and mirrors the control flow
+  const int l16 = lane & 15;
+  const bool lower = lane < 16;
   const int max_it = (int)P(s, MP_SOLVER_ITERS);
   const float thresh = P(s, MP_RESIDUAL_THRESH);
   for (int it = 0; it < max_it; ++it) {
     float resid = 0.f;
-    for (int r = 0; r < n_nc; ++r) {  // motors / limits: J = +-e_j
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {  // motors
+      float d = m_rhs - dv * m_invd;                       // meaningful in lane j (its dv IS dv[j])
+      const float sum = fminf(fmaxf(m_lam + d, -max_imp), max_imp);
+      d = sum - m_lam;
+      if (lane == j) m_lam = sum;
+      const float dj = __shfl_sync(FULL, d, j);
+      dv = fmaf(mrow[j], dj, dv);
+      const float res = dj * mdiag[j];
+      resid = fmaxf(resid, res * res);
+    }
+    for (int r = NL; r < n_nc; ++r) {  // violated joint limits: J = +-e_j
       const int jj = s.ncj[r];
       const int j = abs(jj) - 1;
       const float sgn = jj > 0 ? 1.f : -1.f;
@@ -659,20 +685,20 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
       d = sum - old;
       s.lam[r] = sum;
       if (lane < NL) dv += sgn * s.Minv[lane * NL + j] * d;
-      const float res = d / invd;
+      const float res = d * s.Minv[j * NL + j];
       resid = fmaxf(resid, res * res);
     }
     for (int r = 0; r < nc; ++r) {  // contact normals
       const int row = MAXNC + r;
       const float invd = s.invd[row];
-      const float jd = warp_sum16(lane < 16 ? s.J[r][lane & 15] * dv : 0.f);
+      const float jd = warp_sum16(lower ? s.J[r][l16] * dv : 0.f);
       float d = s.rhs[row] - __shfl_sync(FULL, jd, 0) * invd;
       const float old = s.lam[row];
       const float sum = fmaxf(old + d, 0.f);
       d = sum - old;
       s.lam[row] = sum;
-      if (lane < 16) dv += s.W[r][lane] * d;
-      const float res = d / invd;
+      if (lower) dv = fmaf(s.W[r][l16], d, dv);
+      const float res = d * s.diag[row];
       resid = fmaxf(resid, res * res);
     }
     for (int c = 0; c < nc; ++c) {  // friction cones
@@ -680,21 +706,21 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
       const int rowa = MAXNC + ra, rowb = MAXNC + rb;
       const float lim = s.cmu[c] * s.lam[MAXNC + c];
       const float ia = s.invd[rowa], ib = s.invd[rowb];
-      float ja = lane < 16 ? s.J[ra][lane & 15] * dv : 0.f;
-      float jb = lane < 16 ? s.J[rb][lane & 15] * dv : 0.f;
+      float ja = lower ? s.J[ra][l16] * dv : 0.f;
+      float jb = lower ? s.J[rb][l16] * dv : 0.f;
       ja = __shfl_sync(FULL, warp_sum16(ja), 0);
       jb = __shfl_sync(FULL, warp_sum16(jb), 0);
       const float oa = s.lam[rowa], ob = s.lam[rowb];
       float sa = oa + (s.rhs[rowa] - ja * ia), sb = ob + (s.rhs[rowb] - jb * ib);
-      const float nrm = sqrtf(sa * sa + sb * sb);
-      if (nrm > lim) {
-        const float sc = nrm > 0.f ? lim / nrm : 0.f;
+      const float n2 = sa * sa + sb * sb;
+      if (n2 > lim * lim) {
+        const float sc = n2 > 0.f ? lim * rsqrtf(n2) : 0.f;
         sa *= sc; sb *= sc;
       }
       const float da = sa - oa, db = sb - ob;
       s.lam[rowa] = sa; s.lam[rowb] = sb;
-      if (lane < 16) dv += s.W[ra][lane] * da + s.W[rb][lane] * db;
-      const float r1 = da / ia, r2 = db / ib;
+      if (lower) dv = fmaf(s.W[ra][l16], da, fmaf(s.W[rb][l16], db, dv));
+      const float r1 = da * s.diag[rowa], r2 = db * s.diag[rowb];
       resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
     }
     if (resid <= thresh) break;
@@ -801,7 +827,7 @@ __device__ __forceinline__ void store_state(const Smem& s, float* __restrict__ s
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) env_step_kernel(const float* __restrict__ model_g, EnvParams ep,
+__global__ void __launch_bounds__(32, 16) env_step_kernel(const float* __restrict__ model_g, EnvParams ep,
                                                       float* __restrict__ state, const float* __restrict__ actions,
                                                       float* __restrict__ obs, float* __restrict__ ag,
                                                       float* __restrict__ reward, float* __restrict__ success) {

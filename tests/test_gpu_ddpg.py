@@ -147,7 +147,9 @@ def test_forty_updates_and_polyak_vs_torch_oracle():
                       (T.tc, do.flat_params(L.critic_t))):
         m, r_ = mine.cpu().numpy(), ref.numpy()
         assert np.linalg.norm(m - r_) <= 1e-3 * np.linalg.norm(r_)
-        assert np.abs(m - r_).max() <= 1e-3 * np.abs(r_).max()
+        # Adam moves every element by ~lr per step whatever the gradient's size, so an element whose
+        # gradient is rounding noise can drift by a few steps of lr = 1e-3 between two fp32 back-ends
+        assert np.abs(m - r_).max() <= 5e-3
     T.close()
 
 
