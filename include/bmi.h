@@ -185,6 +185,9 @@ typedef struct bmi_ddpg_config {
   float adam_beta2;   /* 0.999 */
   float adam_eps;     /* 1e-8 */
   float clip_return;  /* 1/(1-gamma) evaluated in double by the caller (ddpg_agent.py:259): 50 */
+  float one_minus_polyak; /* (1 - polyak) evaluated in double by the caller, as python does
+                             (ddpg_agent.py:222), then rounded once to float32: 0.05f */
+  float _pad;
 } bmi_ddpg_config;
 
 int64_t bmi_ddpg_actor_param_count(const bmi_ddpg_config* cfg);

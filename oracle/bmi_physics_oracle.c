@@ -32,7 +32,8 @@
 #define NL 9
 #define NU 15 /* generalized velocities: 9 joints + block linear 3 + block angular 3 */
 #define MAX_ROWS 192
-#define MAX_CONTACTS 48
+#define MAX_CONTACTS 12      /* contacts per sub-step (same caps as the kernel: csrc/physics.cu MAXC / MAXA) */
+#define MAX_ARM_CONTACTS 8   /* ... of which at most 8 involve an arm link; later candidates are dropped */
 #define MAX_SHAPE_V 32
 #define MAX_SHAPE_P 64
 
@@ -366,7 +367,7 @@ static int select_deepest(const double* dist, int n, double margin, int cap, int
 
 static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C) {
   const Model* m = &e->m;
-  int nc = 0;
+  int nc = 0, na = 0;
   double Rb[9], bv[8][3];
   quat_to_mat(Rb, s->bq);
   block_vertices(e, s, Rb, bv);
@@ -394,8 +395,9 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
       int sel[MAX_SHAPE_V];
       for (int i = 0; i < nv; ++i) d[i] = wv[i][2] - tz;
       int n = select_deepest(d, nv, m->P[MP_CONTACT_MARGIN], 2, sel);
-      for (int i = 0; i < n; ++i) {
+      for (int i = 0; i < n && nc < MAX_CONTACTS && na < MAX_ARM_CONTACTS; ++i) {
         Contact* c = &C[nc++];
+        ++na;
         c->link = l; c->has_block = 0; v3cpy(c->x, wv[sel[i]]); v3set(c->n, 0, 0, 1);
         c->dist = d[sel[i]]; c->mu = m->s_mu[sidx] * m->P[MP_MU_TABLE];
       }
@@ -435,9 +437,10 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
     }
     int sel[8 + MAX_SHAPE_V];
     int n = select_deepest(d, 8 + nv, m->P[MP_BLOCK_MARGIN], 3, sel);
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n && nc < MAX_CONTACTS && na < MAX_ARM_CONTACTS; ++i) {
       int ci = sel[i];
       Contact* c = &C[nc++];
+      ++na;
       c->link = l; c->has_block = 1;
       v3cpy(c->x, ci < 8 ? bv[ci] : wv[ci - 8]);
       v3cpy(c->n, nrm[ci]); /* normal from the link (body 2) towards the block (body 1) */

@@ -38,7 +38,7 @@ class DdpgConfig(Structure):
                 ("action_max", c_float), ("gamma", c_float), ("action_l2", c_float),
                 ("lr_actor", c_float), ("lr_critic", c_float), ("polyak", c_float),
                 ("adam_beta1", c_float), ("adam_beta2", c_float), ("adam_eps", c_float),
-                ("clip_return", c_float)]
+                ("clip_return", c_float), ("one_minus_polyak", c_float), ("_pad", c_float)]
 
 
 # name -> (restype, argtypes); every symbol here must be declared in include/bmi.h

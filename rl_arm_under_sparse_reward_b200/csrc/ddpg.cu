@@ -597,7 +597,7 @@ extern "C" int bmi_ddpg_soft_update(bmi_ddpg* h, bmi_stream_t stream) {
   BMI_REQUIRE(h, "bmi_ddpg_soft_update: null handle");
   cudaStream_t st = as_stream(stream);
   // (1 - polyak) is evaluated in double by python, then rounded to f32 when it meets the tensor
-  const float c_src = (float)(1.0 - (double)h->cfg.polyak), c_tgt = h->cfg.polyak;
+  const float c_src = h->cfg.one_minus_polyak, c_tgt = h->cfg.polyak;
   polyak_kernel<<<(unsigned)((h->la.count + 255) / 256), 256, 0, st>>>(h->actor_t, h->actor, h->la.count, c_src, c_tgt);
   BMI_LAUNCHED();
   polyak_kernel<<<(unsigned)((h->lc.count + 255) / 256), 256, 0, st>>>(h->critic_t, h->critic, h->lc.count, c_src, c_tgt);

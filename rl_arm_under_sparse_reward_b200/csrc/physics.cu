@@ -25,9 +25,9 @@ namespace bmi {
 constexpr int NL = 9;          // links / joints of the right arm
 constexpr int NU = 15;         // generalized velocities: 9 joints + block linear 3 + angular 3
 constexpr int EE = 8;          // right_hand2
-constexpr int MAXC = 16;       // contacts per sub-step
+constexpr int MAXC = 12;       // contacts per sub-step
+constexpr int MAXA = 8;        // ... of which at most 8 involve an arm link
 constexpr int MAXNC = 17;      // non-contact rows: 9 motors + up to 8 limit rows
-constexpr int MAXR = MAXNC + 3 * MAXC;
 constexpr int STAGED = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;  // floats staged by TMA
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -51,8 +51,12 @@ struct __align__(16) Smem {
   int clink[MAXC], chasb[MAXC];
   int nc;
   // rows
-  float J[3 * MAXC][16], W[3 * MAXC][16];
-  float invd[MAXR], diag[MAXR], rhs[MAXR], lo[MAXR], hi[MAXR], lam[MAXR];
+  float4 rd[3 * MAXC][4];              // per contact row: Jb[6] Wb[6] | invd rhs diag mu
+  float Ja[3 * MAXA][NL], Wa[3 * MAXA][NL];  // arm parts (only contacts that touch an arm link)
+  int carm[MAXC];                      // arm slot of a contact or -1
+  int na;
+  float lam[3 * MAXC];
+  float invd[MAXNC], rhs[MAXNC], lo[MAXNC], hi[MAXNC], lamn[MAXNC];  // non-contact rows
   int ncj[MAXNC];                 // joint index (+1, sign = direction) of each non-contact row
   // IK scratch
   float A[NL * NL], b[NL], qik[NL];
@@ -357,23 +361,30 @@ __device__ __forceinline__ unsigned select_deepest(float d, bool valid, float ma
 __device__ __forceinline__ void push_contacts(Smem& s, unsigned mask, int lane, int link, int hasb, const float* x,
                                               const float* n, float dist, float mu) {
   if (mask == 0) return;
-  const int base = s.nc;
-  const int slot = base + __popc(mask & ((1u << lane) - 1));
-  if ((mask >> lane) & 1u) {
-    if (slot < MAXC) {
-      s.cx[slot][0] = x[0]; s.cx[slot][1] = x[1]; s.cx[slot][2] = x[2];
-      s.cn[slot][0] = n[0]; s.cn[slot][1] = n[1]; s.cn[slot][2] = n[2];
-      s.cdist[slot] = dist; s.cmu[slot] = mu; s.clink[slot] = link; s.chasb[slot] = hasb;
-    }
+  const int base = s.nc, abase = s.na;
+  // capacity: MAXC contacts in total, MAXA of them on arm links; later candidates (lane order) are dropped
+  int allowed = MAXC - base;
+  if (link >= 0) allowed = min(allowed, MAXA - abase);
+  const int rank = __popc(mask & ((1u << lane) - 1));
+  const int n_add = min(__popc(mask), max(allowed, 0));
+  if (((mask >> lane) & 1u) && rank < n_add) {
+    const int slot = base + rank;
+    s.cx[slot][0] = x[0]; s.cx[slot][1] = x[1]; s.cx[slot][2] = x[2];
+    s.cn[slot][0] = n[0]; s.cn[slot][1] = n[1]; s.cn[slot][2] = n[2];
+    s.cdist[slot] = dist; s.cmu[slot] = mu; s.clink[slot] = link; s.chasb[slot] = hasb;
+    s.carm[slot] = link >= 0 ? abase + rank : -1;
   }
   __syncwarp();
-  if (lane == 0) s.nc = min(MAXC, base + __popc(mask));
+  if (lane == 0) {
+    s.nc = base + n_add;
+    if (link >= 0) s.na = abase + n_add;
+  }
   __syncwarp();
 }
 
 __device__ void find_contacts(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, float block_margin,
                               int lane) {
-  if (lane == 0) s.nc = 0;
+  if (lane == 0) { s.nc = 0; s.na = 0; }
   // block frame
   if (lane == 0) {
     const float x = s.bq[0], y = s.bq[1], z = s.bq[2], w = s.bq[3];
@@ -548,7 +559,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
     const float target = P(s, MP_MOTOR_KP) * (s.qt[lane] - s.q[lane]) / dt + (1.f - P(s, MP_MOTOR_KD)) * s.qd[lane];
     s.invd[lane] = 1.f / w;
     s.rhs[lane] = (target - s.u[lane]) / w;
-    s.lo[lane] = -max_imp; s.hi[lane] = max_imp; s.lam[lane] = 0.f;
+    s.lo[lane] = -max_imp; s.hi[lane] = max_imp; s.lamn[lane] = 0.f;
     s.ncj[lane] = lane + 1;
   }
   {
@@ -567,13 +578,16 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
       const float w = s.Minv[j * NL + j];
       s.invd[slot] = 1.f / w;
       s.rhs[slot] = (-pen * P(s, MP_ERP_JOINT) / dt - sgn * s.u[j]) / w;
-      s.lo[slot] = 0.f; s.hi[slot] = P(s, MP_JOINT_LIMIT_IMPULSE); s.lam[slot] = 0.f;
+      s.lo[slot] = 0.f; s.hi[slot] = P(s, MP_JOINT_LIMIT_IMPULSE); s.lamn[slot] = 0.f;
       s.ncj[slot] = side == 0 ? (j + 1) : -(j + 1);
     }
     n_nc = min(MAXNC, NL + __popc(m));
   }
   __syncwarp();
   // ---- contact rows: lane = row (3 rows per contact: normal, tangent 1, tangent 2) ------------------
+  // Row storage: the block part of every row (J and M^-1 J^T over the block's 6 velocities) plus its scalars is
+  // one 64-byte record read with broadcast LDS.128; the arm part (9 + 9 floats) exists only for contacts that
+  // touch an arm link.
   const int nc = s.nc;
   const int n_rows_c = 3 * nc;
   for (int base = 0; base < n_rows_c; base += 32) {
@@ -596,6 +610,9 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
 #pragma unroll
         for (int a = 0; a < 3; ++a) { J[9 + a] = dir[a]; J[12 + a] = t[a]; }
       }
+      float Wv[NU];
+#pragma unroll
+      for (int i = 0; i < NL; ++i) Wv[i] = 0.f;
       if (link >= 0) {
         const float sgn = hasb ? -1.f : 1.f;
 #pragma unroll
@@ -608,14 +625,16 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
             J[j] = sgn * dot3(dir, cr);
           }
         }
-      }
-      float Wv[NU];
 #pragma unroll
-      for (int i = 0; i < NL; ++i) {
-        float acc = 0.f;
+        for (int i = 0; i < NL; ++i) {
+          float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < NL; ++j) acc += s.Minv[i * NL + j] * J[j];
-        Wv[i] = acc;
+          for (int j = 0; j < NL; ++j) acc += s.Minv[i * NL + j] * J[j];
+          Wv[i] = acc;
+        }
+        const int as = s.carm[ci] * 3 + kind;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) { s.Ja[as][i] = J[i]; s.Wa[as][i] = Wv[i]; }
       }
 #pragma unroll
       for (int a = 0; a < 3; ++a) Wv[9 + a] = J[9 + a] / ep.bmass;
@@ -624,28 +643,30 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
 #pragma unroll
       for (int a = 0; a < NU; ++a) { diag += J[a] * Wv[a]; rel += J[a] * s.u[a]; }
       const float invd = 1.f / diag;
-#pragma unroll
-      for (int a = 0; a < NU; ++a) { s.J[ri][a] = J[a]; s.W[ri][a] = Wv[a]; }
-      s.J[ri][15] = 0.f; s.W[ri][15] = 0.f;
-      const int row = MAXNC + ri;
-      s.invd[row] = invd; s.diag[row] = diag; s.lam[row] = 0.f;
+      float rhs;
       if (kind == 0) {
         const float pen = s.cdist[ci] + P(s, MP_LINEAR_SLOP);
         float pos_err = 0.f, vel_err = -rel;
         if (pen > 0.f) vel_err -= pen / dt; else pos_err = -pen * P(s, MP_ERP_CONTACT) / dt;
-        s.rhs[row] = (pos_err + vel_err) * invd;
-        s.lo[row] = 0.f; s.hi[row] = 1e10f;
+        rhs = (pos_err + vel_err) * invd;
       } else {
-        s.rhs[row] = -rel * invd;
-        s.lo[row] = 0.f; s.hi[row] = 0.f;
+        rhs = -rel * invd;
       }
+      s.rd[ri][0] = make_float4(J[9], J[10], J[11], J[12]);
+      s.rd[ri][1] = make_float4(J[13], J[14], Wv[9], Wv[10]);
+      s.rd[ri][2] = make_float4(Wv[11], Wv[12], Wv[13], Wv[14]);
+      s.rd[ri][3] = make_float4(invd, rhs, diag, s.cmu[ci]);
+      s.lam[ri] = 0.f;
     }
   }
   __syncwarp();
-  // ---- projected Gauss-Seidel; lane d holds dv[d] -------------------------------------------------------
-  // Motor rows (always 9, J = e_j) live entirely in registers: lane j owns row j's rhs / 1/diag / lambda and
-  // every lane < 9 keeps its row of M^-1 (mrow[j] = Minv[lane][j]); one shuffle broadcasts dv[j].
+  // ---- projected Gauss-Seidel ---------------------------------------------------------------------------
+  // Velocity deltas: lane j < 9 owns the arm's dv[j]; the block's six deltas are REPLICATED in every lane
+  // (dvb), so block-only rows (block on table: the common case) need no cross-lane traffic at all.
+  // Motor rows (always 9, J = e_j) live in registers: lane j owns row j's rhs / 1/diag / lambda and every lane
+  // keeps its row of M^-1 (mrow[j] = Minv[lane][j]); one shuffle per motor row broadcasts the impulse.
   float dv = 0.f;
+  float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float mrow[NL];
 #pragma unroll
   for (int j = 0; j < NL; ++j) mrow[j] = lane < NL ? s.Minv[lane * NL + j] : 0.f;
@@ -655,12 +676,25 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   float mdiag[NL];
 #pragma unroll
   for (int j = 0; j < NL; ++j) mdiag[j] = __shfl_sync(FULL, m_diag, j);
-  // lanes 0..15 use both halves of the warp for contact rows: the 16-lane butterfly already leaves the dot
-  // product in every lane of the lower half; the upper half holds zeros and mirrors the control flow
-  const int l16 = lane & 15;
-  const bool lower = lane < 16;
+  const bool arm_lane = lane < NL;
   const int max_it = (int)P(s, MP_SOLVER_ITERS);
   const float thresh = P(s, MP_RESIDUAL_THRESH);
+  // J_r . dv for contact row r of contact c (kind 0/1/2): block part from registers, arm part by shuffle-reduce
+  auto row_dot = [&](const float4& r0, const float4& r1, int as_row) -> float {
+    float d0 = r0.x * dvb[0] + r0.y * dvb[1] + r0.z * dvb[2];
+    float d1 = r0.w * dvb[3] + r1.x * dvb[4] + r1.y * dvb[5];
+    float dot = d0 + d1;
+    if (as_row >= 0) {  // uniform branch
+      const float t = arm_lane ? s.Ja[as_row][lane] * dv : 0.f;
+      dot += __shfl_sync(FULL, warp_sum16(t), 0);
+    }
+    return dot;
+  };
+  auto row_apply = [&](const float4& r1, const float4& r2, int as_row, float d) {
+    dvb[0] = fmaf(r1.z, d, dvb[0]); dvb[1] = fmaf(r1.w, d, dvb[1]); dvb[2] = fmaf(r2.x, d, dvb[2]);
+    dvb[3] = fmaf(r2.y, d, dvb[3]); dvb[4] = fmaf(r2.z, d, dvb[4]); dvb[5] = fmaf(r2.w, d, dvb[5]);
+    if (as_row >= 0 && arm_lane) dv = fmaf(s.Wa[as_row][lane], d, dv);
+  };
   for (int it = 0; it < max_it; ++it) {
     float resid = 0.f;
 #pragma unroll
@@ -680,54 +714,57 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
       const float sgn = jj > 0 ? 1.f : -1.f;
       const float invd = s.invd[r];
       float d = s.rhs[r] - sgn * __shfl_sync(FULL, dv, j) * invd;
-      const float old = s.lam[r];
+      const float old = s.lamn[r];
       float sum = fminf(fmaxf(old + d, s.lo[r]), s.hi[r]);
       d = sum - old;
-      s.lam[r] = sum;
-      if (lane < NL) dv += sgn * s.Minv[lane * NL + j] * d;
+      s.lamn[r] = sum;
+      if (arm_lane) dv += sgn * s.Minv[lane * NL + j] * d;
       const float res = d * s.Minv[j * NL + j];
       resid = fmaxf(resid, res * res);
     }
-    for (int r = 0; r < nc; ++r) {  // contact normals
-      const int row = MAXNC + r;
-      const float invd = s.invd[row];
-      const float jd = warp_sum16(lower ? s.J[r][l16] * dv : 0.f);
-      float d = s.rhs[row] - __shfl_sync(FULL, jd, 0) * invd;
-      const float old = s.lam[row];
+    for (int c = 0; c < nc; ++c) {  // contact normals
+      const float4 r0 = s.rd[c][0], r1 = s.rd[c][1], r2 = s.rd[c][2], r3 = s.rd[c][3];
+      const int as = s.carm[c];
+      const int asr = as >= 0 ? as * 3 : -1;
+      float d = r3.y - row_dot(r0, r1, asr) * r3.x;
+      const float old = s.lam[c];
       const float sum = fmaxf(old + d, 0.f);
       d = sum - old;
-      s.lam[row] = sum;
-      if (lower) dv = fmaf(s.W[r][l16], d, dv);
-      const float res = d * s.diag[row];
+      s.lam[c] = sum;
+      row_apply(r1, r2, asr, d);
+      const float res = d * r3.z;
       resid = fmaxf(resid, res * res);
     }
     for (int c = 0; c < nc; ++c) {  // friction cones
       const int ra = nc + 2 * c, rb = ra + 1;
-      const int rowa = MAXNC + ra, rowb = MAXNC + rb;
-      const float lim = s.cmu[c] * s.lam[MAXNC + c];
-      const float ia = s.invd[rowa], ib = s.invd[rowb];
-      float ja = lower ? s.J[ra][l16] * dv : 0.f;
-      float jb = lower ? s.J[rb][l16] * dv : 0.f;
-      ja = __shfl_sync(FULL, warp_sum16(ja), 0);
-      jb = __shfl_sync(FULL, warp_sum16(jb), 0);
-      const float oa = s.lam[rowa], ob = s.lam[rowb];
-      float sa = oa + (s.rhs[rowa] - ja * ia), sb = ob + (s.rhs[rowb] - jb * ib);
+      const float4 a0 = s.rd[ra][0], a1 = s.rd[ra][1], a2 = s.rd[ra][2], a3 = s.rd[ra][3];
+      const float4 b0 = s.rd[rb][0], b1 = s.rd[rb][1], b2 = s.rd[rb][2], b3 = s.rd[rb][3];
+      const int as = s.carm[c];
+      const int asa = as >= 0 ? as * 3 + 1 : -1, asb = as >= 0 ? as * 3 + 2 : -1;
+      const float lim = a3.w * s.lam[c];
+      const float ja = row_dot(a0, a1, asa), jb = row_dot(b0, b1, asb);
+      const float oa = s.lam[ra], ob = s.lam[rb];
+      float sa = oa + (a3.y - ja * a3.x), sb = ob + (b3.y - jb * b3.x);
       const float n2 = sa * sa + sb * sb;
       if (n2 > lim * lim) {
         const float sc = n2 > 0.f ? lim * rsqrtf(n2) : 0.f;
         sa *= sc; sb *= sc;
       }
       const float da = sa - oa, db = sb - ob;
-      s.lam[rowa] = sa; s.lam[rowb] = sb;
-      if (lower) dv = fmaf(s.W[ra][l16], da, fmaf(s.W[rb][l16], db, dv));
-      const float r1 = da * s.diag[rowa], r2 = db * s.diag[rowb];
-      resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
+      s.lam[ra] = sa; s.lam[rb] = sb;
+      row_apply(a1, a2, asa, da);
+      row_apply(b1, b2, asb, db);
+      const float r1_ = da * a3.z, r2_ = db * b3.z;
+      resid = fmaxf(resid, fmaxf(r1_ * r1_, r2_ * r2_));
     }
     if (resid <= thresh) break;
   }
   __syncwarp();
   // ---- integrate ----------------------------------------------------------------------------------------
-  const float unew = (lane < 16 ? s.u[lane & 15] : 0.f) + dv;
+  float dvl = dv;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) if (lane == 9 + k) dvl = dvb[k];
+  const float unew = (lane < 16 ? s.u[lane & 15] : 0.f) + dvl;
   if (lane < NL) {
     s.qd[lane] = unew;
     s.q[lane] += dt * unew;

@@ -50,7 +50,8 @@ class ddpg_agent:
         self.critic_target_network.flat.copy_(self.critic_network.flat)
         cfg = _lib.DdpgConfig(Do, Dg, Da, 256, int(args.batch_size), max(self.R, 1), float(env_params['action_max']),
                               float(args.gamma), float(args.action_l2), float(args.lr_actor), float(args.lr_critic),
-                              float(args.polyak), 0.9, 0.999, 1e-8, float(1.0 / (1.0 - args.gamma)))
+                              float(args.polyak), 0.9, 0.999, 1e-8, float(1.0 / (1.0 - args.gamma)),
+                              float(1.0 - args.polyak), 0.0)
         self._cfg = cfg
         h = ctypes.c_void_p()
         _lib.call("bmi_ddpg_create", ctypes.byref(h), ctypes.byref(cfg), _lib.ptr(self.actor_network.flat),

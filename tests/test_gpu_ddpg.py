@@ -39,7 +39,7 @@ class Trainer:
         self.ta = do.flat_params(L.actor_t).to(dev).contiguous()
         self.tc = do.flat_params(L.critic_t).to(dev).contiguous()
         self.cfg = _lib.DdpgConfig(27, 3, 4, 256, batch, max_rows, 0.5, 0.98, 1.0, 1e-3, 1e-3, 0.95, 0.9, 0.999, 1e-8,
-                                   float(1.0 / (1.0 - 0.98)))
+                                   float(1.0 / (1.0 - 0.98)), float(1.0 - 0.95), 0.0)
         self.h = ctypes.c_void_p()
         _lib.call("bmi_ddpg_create", ctypes.byref(self.h), ctypes.byref(self.cfg), _lib.ptr(self.pa), _lib.ptr(self.pc),
                   _lib.ptr(self.ta), _lib.ptr(self.tc))
