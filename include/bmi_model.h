@@ -37,7 +37,8 @@ enum {
   MP_PUSH_HX = 32, MP_PUSH_HY = 33, MP_PUSH_HZ = 34, MP_PUSH_MASS = 35, MP_PUSH_MU = 36,
   MP_PICK_HX = 37, MP_PICK_HY = 38, MP_PICK_HZ = 39, MP_PICK_MASS = 40, MP_PICK_MU = 41,
   MP_DIST_THRESHOLD = 42, MP_JOINT_LIMIT_IMPULSE = 43, MP_BLOCK_MARGIN = 44, MP_TABLE_MARGIN = 45,
-  MP_IK_POS_AT_COM = 46, MP_SELF_COLLISION = 47
+  MP_IK_POS_AT_COM = 46, MP_SELF_COLLISION = 47,
+  MP_WARMSTART = 48       /* contact warm-starting factor (Bullet default 0.85); 0 disables */
 };
 
 /* per-link slots (BMI_LINK_STRIDE floats each) */

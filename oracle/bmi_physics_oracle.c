@@ -51,6 +51,10 @@ typedef struct {
   double q[NL], qd[NL], qt[NL];
   double bp[3], bq[4], bv[3], bw[3];
   double goal[3];
+  /* warm-start cache: contacts of the previous sub-step (slot id, normal + two friction impulses) */
+  int wn, wid[MAX_CONTACTS];
+  double wl[MAX_CONTACTS][3];
+  double wm[NL]; /* motor impulses of the previous sub-step */
 } State;
 
 typedef struct {
@@ -59,6 +63,7 @@ typedef struct {
   double bh[3], bmass, binertia[3], bmu; /* block half extents / mass / diagonal inertia / friction */
   /* statistics of the last step (for tests / tuning) */
   int last_rows, last_iters, last_contacts;
+  double resid_hist[256]; int worst_row[256];
 } Env;
 
 /* ------------------------------------------------------------------ small vector helpers */
@@ -339,6 +344,7 @@ typedef struct {
   int link;     /* arm link index or -1 (static world) */
   int has_block;/* 1: body 1 is the block */
   double x[3], n[3], dist, mu;
+  int id;       /* candidate slot: block vertex 0..7 | 8 + 32 shape + hull vertex | 136 + 32 shape + candidate */
 } Contact;
 
 static void block_vertices(const Env* e, const State* s, const double* Rb, double v[8][3]) {
@@ -380,7 +386,7 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
     int n = select_deepest(d, 8, m->P[MP_TABLE_MARGIN], 4, sel);
     for (int i = 0; i < n; ++i) {
       Contact* c = &C[nc++];
-      c->link = -1; c->has_block = 1; v3cpy(c->x, bv[sel[i]]); v3set(c->n, 0, 0, 1);
+      c->link = -1; c->has_block = 1; c->id = sel[i]; v3cpy(c->x, bv[sel[i]]); v3set(c->n, 0, 0, 1);
       c->dist = d[sel[i]]; c->mu = e->bmu * m->P[MP_MU_TABLE];
     }
   }
@@ -398,7 +404,7 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
       for (int i = 0; i < n && nc < MAX_CONTACTS && na < MAX_ARM_CONTACTS; ++i) {
         Contact* c = &C[nc++];
         ++na;
-        c->link = l; c->has_block = 0; v3cpy(c->x, wv[sel[i]]); v3set(c->n, 0, 0, 1);
+        c->link = l; c->has_block = 0; c->id = 8 + 32 * sidx + sel[i]; v3cpy(c->x, wv[sel[i]]); v3set(c->n, 0, 0, 1);
         c->dist = d[sel[i]]; c->mu = m->s_mu[sidx] * m->P[MP_MU_TABLE];
       }
     }
@@ -441,7 +447,7 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
       int ci = sel[i];
       Contact* c = &C[nc++];
       ++na;
-      c->link = l; c->has_block = 1;
+      c->link = l; c->has_block = 1; c->id = 136 + 32 * sidx + ci;
       v3cpy(c->x, ci < 8 ? bv[ci] : wv[ci - 8]);
       v3cpy(c->n, nrm[ci]); /* normal from the link (body 2) towards the block (body 1) */
       c->dist = d[ci]; c->mu = e->bmu * m->s_mu[sidx];
@@ -592,6 +598,25 @@ static void substep(Env* e, State* s) {
   }
   /* ---- projected Gauss-Seidel (Bullet order: non-contact, normals, friction cones) ---- */
   double dv[NU] = {0};
+  { /* warm start (Bullet SOLVER_USE_WARMSTARTING): contacts that persist from the previous sub-step start from
+       warmstart_factor x their last impulses; motors and limits start from zero */
+    const double wf = m->P[MP_WARMSTART];
+    for (int j = 0; j < NL && wf > 0; ++j) { /* motor rows are rows 0..8 */
+      Row* r = &rows[j];
+      r->lambda = fmin(fmax(wf * s->wm[j], r->lo), r->hi);
+      for (int a = 0; a < NU; ++a) dv[a] += r->W[a] * r->lambda;
+    }
+    for (int ci = 0; ci < nc && wf > 0; ++ci)
+      for (int w = 0; w < s->wn; ++w)
+        if (s->wid[w] == C[ci].id) {
+          Row* rn = &rows[normal_row[ci]];
+          Row* ra = &rows[n_normal_end + 2 * ci];
+          Row* rb = ra + 1;
+          rn->lambda = wf * s->wl[w][0]; ra->lambda = wf * s->wl[w][1]; rb->lambda = wf * s->wl[w][2];
+          for (int a = 0; a < NU; ++a) dv[a] += rn->W[a] * rn->lambda + ra->W[a] * ra->lambda + rb->W[a] * rb->lambda;
+          break;
+        }
+  }
   const int max_it = (int)m->P[MP_SOLVER_ITERS];
   int it;
   for (it = 0; it < max_it; ++it) {
@@ -622,9 +647,18 @@ static void substep(Env* e, State* s) {
       if (r1 * r1 > resid) resid = r1 * r1;
       if (r2 * r2 > resid) resid = r2 * r2;
     }
+    if (it < 256) e->resid_hist[it] = resid;
     if (resid <= m->P[MP_RESIDUAL_THRESH]) { ++it; break; }
   }
   e->last_rows = nr; e->last_iters = it; e->last_contacts = nc;
+  s->wn = nc;
+  for (int j = 0; j < NL; ++j) s->wm[j] = rows[j].lambda;
+  for (int ci = 0; ci < nc; ++ci) {
+    s->wid[ci] = C[ci].id;
+    s->wl[ci][0] = rows[normal_row[ci]].lambda;
+    s->wl[ci][1] = rows[n_normal_end + 2 * ci].lambda;
+    s->wl[ci][2] = rows[n_normal_end + 2 * ci + 1].lambda;
+  }
   (void)n_noncontact;
   /* ---- integrate ---- */
   for (int i = 0; i < NL; ++i) { s->qd[i] = u[i] + dv[i]; s->q[i] += dt * s->qd[i]; }
@@ -791,3 +825,5 @@ void bmo_mass_matrix(void* hp, const double* q, double* M81) {
     for (int i = 0; i < NL; ++i) M81[i * NL + j] = col[i];
   }
 }
+
+void bmo_resid_hist(void* hp, double* out256) { memcpy(out256, ((Handle*)hp)->env.resid_hist, sizeof(double) * 256); }

@@ -45,7 +45,7 @@ P = dict(magic=0, version=1, n_links=2, n_shapes=3, links_off=4, shapes_off=5, p
          push_hx=32, push_hy=33, push_hz=34, push_mass=35, push_mu=36,
          pick_hx=37, pick_hy=38, pick_hz=39, pick_mass=40, pick_mu=41,
          dist_threshold=42, joint_limit_force=43, block_margin=44, table_margin=45, ik_pos_at_com=46,
-         self_collision=47)
+         self_collision=47, warmstart=48)
 L = dict(parent=0, jpos=1, jrot=4, axis=13, lo=16, hi=17, damping=18, mass=19, com=20, inertia=23, shape=26, mu=27)
 
 
@@ -200,6 +200,7 @@ def main(k_verts=24):
     hdr[P["block_margin"]], hdr[P["table_margin"]] = 0.002, 0.0
     hdr[P["ik_pos_at_com"]] = 0.0
     hdr[P["self_collision"]] = 0.0
+    hdr[P["warmstart"]] = 0.0   # 0.85 (Bullet default) is implemented in the oracle only; the kernel does not warm-start yet
 
     blob = np.concatenate([hdr, blob_links.reshape(-1), np.array(shapes, np.float64).reshape(-1), np.array(pool)])
     assert blob.shape[0] == int(hdr[P["total"]])
