@@ -257,6 +257,28 @@ int bmi_env_sample_init(bmi_env* h, uint64_t seed, uint64_t* counter_dev, float*
  * stepSimulation, observation, sparse reward, is_success.  All arrays float32 device. */
 int bmi_env_step(bmi_env* h, const float* actions_dev, float* obs_dev, float* ag_dev,
                  float* reward_dev, float* success_dev, bmi_stream_t stream);
+/* Fused rollout (ddpg_agent.py:103-141 for all envs in ONE launch): reset from `init`, then T times
+ * [record obs/ag/g -> _preproc_inputs -> actor MLP -> _select_actions -> record action -> env step],
+ * then record the final obs/ag.  Each env advances at its own pace (no per-step grid-wide
+ * synchronisation).  The actor weights are read in the transposed layout written by
+ * bmi_actor_transpose; exploration uses the same Philox stream as bmi_select_actions
+ * (counter + t * n_envs + env), so fused and step-wise rollouts draw identical noise. */
+typedef struct bmi_rollout_args {
+  int32_t T;
+  int32_t explore;               /* 0: deterministic policy (evaluation, ddpg_agent.py:280-304) */
+  const float* actor_t;          /* device, transposed actor parameters (same count as the flat buffer) */
+  const float* o_mean; const float* o_std; const float* g_mean; const float* g_std;  /* device */
+  float clip_range, action_max, noise_eps, random_eps, late_clip;
+  uint64_t seed;
+  uint64_t* counter;             /* device Philox counter, advanced by T * n_envs */
+  const bmi_episodes* episodes;  /* float32 rollout staging [n_envs][T+1|T][dim] or NULL */
+  const float* init;             /* device [n_envs][8] placements or NULL (continue from the current state) */
+  float* obs; float* ag; float* g; float* success;   /* device outputs after the last step (may be NULL) */
+} bmi_rollout_args;
+int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* args, bmi_stream_t stream);
+/* torch-layout flat actor parameters (W[out][in], b per layer) -> W^T[in][out], b per layer */
+int bmi_actor_transpose(const float* actor_params_dev, int32_t obs_dim, int32_t goal_dim, int32_t act_dim,
+                        int32_t hidden, float* actor_t_dev, bmi_stream_t stream);
 /* raw per-env simulator state for tests/checkpoints: float32 [n_envs][BMI_ENV_STATE_DIM] */
 #define BMI_ENV_STATE_DIM 48
 int bmi_env_get_state(bmi_env* h, float* state_dev, bmi_stream_t stream);

@@ -41,6 +41,14 @@ class DdpgConfig(Structure):
                 ("clip_return", c_float), ("one_minus_polyak", c_float), ("_pad", c_float)]
 
 
+class RolloutArgs(Structure):
+    _fields_ = [("T", c_int32), ("explore", c_int32), ("actor_t", c_void_p), ("o_mean", c_void_p), ("o_std", c_void_p),
+                ("g_mean", c_void_p), ("g_std", c_void_p), ("clip_range", c_float), ("action_max", c_float),
+                ("noise_eps", c_float), ("random_eps", c_float), ("late_clip", c_float), ("seed", c_uint64),
+                ("counter", c_void_p), ("episodes", POINTER(Episodes)), ("init", c_void_p), ("obs", c_void_p),
+                ("ag", c_void_p), ("g", c_void_p), ("success", c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol here must be declared in include/bmi.h
 SIGNATURES = {
     "bmi_abi_version": (c_int32, []),
@@ -86,6 +94,8 @@ SIGNATURES = {
     "bmi_env_sample_init": (c_int32, [c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]),
     "bmi_env_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "bmi_env_rollout": (c_int32, [c_void_p, POINTER(RolloutArgs), c_void_p]),
+    "bmi_actor_transpose": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "bmi_env_get_state": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "bmi_env_set_state": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "bmi_rollout_record": (c_int32, [POINTER(Episodes), c_int32, c_void_p, c_void_p, c_void_p,

@@ -72,6 +72,26 @@ class BmiVecEnv:
                   _lib.ptr(self.reward), _lib.ptr(self.success), _lib.stream_ptr())
         return self.obs, self.ag, self.reward, self.success
 
+    def rollout(self, T, actor_t, o_norm, g_norm, clip_range, explore, noise_eps=0.0, random_eps=0.0, late_clip=0.0,
+                seed=0, counter=None, episodes=None, reset=True):
+        """Fused rollout: ONE kernel launch runs T policy + env steps for every env (bmi_env_rollout).
+        actor_t: transposed flat actor parameters (bmi_actor_transpose); o_norm/g_norm: normalizer objects;
+        episodes: dict of float32 staging tensors obs/ag/g/actions or None.  Returns (obs, ag, g, success)."""
+        if reset:
+            _lib.call("bmi_env_sample_init", self._h, ctypes.c_uint64(self.seed_value), _lib.ptr(self.counter),
+                      _lib.ptr(self.init), _lib.stream_ptr())
+        eps = None
+        if episodes is not None:
+            eps = _lib.Episodes(_lib.ptr(episodes['obs']), _lib.ptr(episodes['ag']), _lib.ptr(episodes['g']),
+                                _lib.ptr(episodes['actions']), self.n_envs, int(T), 27, 3, 4, _lib.BMI_F32, 0)
+        ra = _lib.RolloutArgs(int(T), int(bool(explore)), _lib.ptr(actor_t), _lib.ptr(o_norm.mean_dev), _lib.ptr(o_norm.std_dev),
+                              _lib.ptr(g_norm.mean_dev), _lib.ptr(g_norm.std_dev), float(clip_range), float(self.action_max),
+                              float(noise_eps), float(random_eps), float(late_clip), int(seed), _lib.ptr(counter),
+                              ctypes.pointer(eps) if eps is not None else None, _lib.ptr(self.init) if reset else None,
+                              _lib.ptr(self.obs), _lib.ptr(self.ag), _lib.ptr(self.g), _lib.ptr(self.success))
+        _lib.call("bmi_env_rollout", self._h, ctypes.byref(ra), _lib.stream_ptr())
+        return self.obs, self.ag, self.g, self.success
+
     def get_state(self):
         st = torch.empty((self.n_envs, _lib.ENV_STATE_DIM), dtype=torch.float32, device=self.device)
         _lib.call("bmi_env_get_state", self._h, _lib.ptr(st), _lib.stream_ptr())

@@ -25,11 +25,16 @@ namespace bmi {
 constexpr int NL = 9;          // links / joints of the right arm
 constexpr int NU = 15;         // generalized velocities: 9 joints + block linear 3 + angular 3
 constexpr int EE = 8;          // right_hand2
-constexpr int MAXC = 12;       // contacts per sub-step
-constexpr int MAXA = 8;        // ... of which at most 8 involve an arm link
+constexpr int MAXC = 10;       // contacts per sub-step
+constexpr int MAXA = 6;        // ... of which at most 6 involve an arm link
 constexpr int MAXNC = 17;      // non-contact rows: 9 motors + up to 8 limit rows
 constexpr int STAGED = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;  // floats staged by TMA
+constexpr int HID = 256;         // hidden width of the actor (models.py:15-17)
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef BMI_BLOCKS_PER_SM
+#define BMI_BLOCKS_PER_SM 7
+#endif
+constexpr int BLOCKS_PER_SM = BMI_BLOCKS_PER_SM;  // x WARPS warps: 28 envs per SM -> 4096 envs resident in one wave
 
 // topology of the right arm: chain 0..6, two fingers on link 6 (checked against the blob)
 __host__ __device__ constexpr int parent_of(int i) { return i == 0 ? -1 : (i <= 6 ? i - 1 : 6); }
@@ -37,13 +42,15 @@ __host__ __device__ constexpr bool is_ancestor_or_self(int a, int l) {
   return a == l || (a <= 6 && l >= a);  // every chain link j<=6 is an ancestor of all l>=j
 }
 
-struct __align__(16) Smem {
-  float model[STAGED];            // header params + link records (TMA destination)
-  unsigned long long mbar;
+constexpr int WARPS = 4;        // env instances (warps) per thread block; they share one staged model copy
+
+struct __align__(16) Smem {      // per-env (per-warp) working set
+  const float* model;             // block-shared header params + link records (the TMA destination)
   float R[NL][9], p[NL][3], z[NL][3], c[NL][3], Rl[NL][9];
   float L[NL * NL], Minv[NL * NL];
   float q[NL], qd[NL], qt[NL], bias[NL], acc[NL];
   float u[16];
+  float tauw[NL + 1][NL];             // per-lane RNEA output rows
   float bp[3], bq[4], bv[3], bw[3], goal[3];
   float Rb[9], Ibinv[9], bvert[8][3];
   // contacts
@@ -51,15 +58,23 @@ struct __align__(16) Smem {
   int clink[MAXC], chasb[MAXC];
   int nc;
   // rows
-  float4 rd[3 * MAXC][4];              // per contact row: Jb[6] Wb[6] | invd rhs diag mu
-  float Ja[3 * MAXA][NL], Wa[3 * MAXA][NL];  // arm parts (only contacts that touch an arm link)
+  union {
+    struct {
+      union {
+        float4 rd[3 * MAXC][4];            // per contact row: Jb[6] Wb[6] | invd rhs diag mu
+        struct { float A[NL * NL], b[NL]; } ik;   // IK scratch (the IK runs before the sub-steps)
+      };
+      float Ja[3 * MAXA][NL], Wa[3 * MAXA][NL];  // arm parts (only contacts that touch an arm link)
+    };
+    struct { float x[32], hA[HID], hB[HID]; } pol;  // policy activations (fused rollout; between env steps)
+  };
+  float obs[BMI_OBS_DIM + BMI_GOAL_DIM];   // last observation + achieved goal (fused rollout)
   int carm[MAXC];                      // arm slot of a contact or -1
   int na;
   float lam[3 * MAXC];
   float invd[MAXNC], rhs[MAXNC], lo[MAXNC], hi[MAXNC], lamn[MAXNC];  // non-contact rows
   int ncj[MAXNC];                 // joint index (+1, sign = direction) of each non-contact row
-  // IK scratch
-  float A[NL * NL], b[NL], qik[NL];
+  float qik[NL];
 };
 
 struct EnvParams {
@@ -94,9 +109,11 @@ __device__ __forceinline__ float warp_sum16(float v) {  // sum over lanes 0..15 
 }
 
 // ---- TMA staging of the joint tree ---------------------------------------------------------
-__device__ __forceinline__ void stage_model(Smem& s, const float* __restrict__ model_g, int lane) {
-  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s.mbar);
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(s.model);
+__device__ __forceinline__ void stage_model(float* model_s, unsigned long long* mbar_s,
+                                            const float* __restrict__ model_g, int tid) {
+  const int lane = tid;  // thread 0 of the block issues the copy; every thread of every warp waits on the barrier
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_s);
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(model_s);
   constexpr unsigned bytes = STAGED * sizeof(float);
   static_assert(bytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
   if (lane == 0) {
@@ -107,7 +124,7 @@ __device__ __forceinline__ void stage_model(Smem& s, const float* __restrict__ m
                  "l"(model_g), "r"(bytes), "r"(mbar)
                  : "memory");
   }
-  __syncwarp();
+  __syncthreads();  // barrier initialised and armed before anyone polls it
   unsigned done = 0;
   while (!done) {
     asm volatile(
@@ -119,7 +136,7 @@ __device__ __forceinline__ void stage_model(Smem& s, const float* __restrict__ m
 }
 
 // ---- forward kinematics ----------------------------------------------------------------------
-__device__ void fk(Smem& s, const float* q, int lane) {
+__device__ __noinline__ void fk(Smem& s, const float* q, int lane) {
   if (lane < NL) {  // local rotation jrot * Rodrigues(axis, q)
     const float* lk = LK(s, lane);
     const float ux = lk[ML_AXIS], uy = lk[ML_AXIS + 1], uz = lk[ML_AXIS + 2];
@@ -137,10 +154,8 @@ __device__ void fk(Smem& s, const float* q, int lane) {
         s.Rl[lane][3 * r + cc] = Jr[3 * r] * Rq[cc] + Jr[3 * r + 1] * Rq[3 + cc] + Jr[3 * r + 2] * Rq[6 + cc];
   }
   __syncwarp();
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < NL; ++i) {
-    constexpr int dummy = 0;
-    (void)dummy;
     const int pa = parent_of(i);
     if (lane < 9) {
       const int r = lane / 3, cc = lane % 3;
@@ -172,14 +187,14 @@ __device__ void fk(Smem& s, const float* q, int lane) {
 // ---- recursive Newton-Euler, one independent sweep per lane ------------------------------------
 // tau_j = z_j . sum_{k in subtree(j)} [ N_k + (c_k - p_j) x F_k ]   (accumulated pairwise so that no
 // per-link force arrays are needed; the tree topology is a compile-time constant).
-__device__ __forceinline__ void rnea_lane(const Smem& s, bool is_bias, int unit, float gz, float kl, float ka,
-                                          float* tau) {
+// Kept as a compact runtime loop (not unrolled): the kernel is instruction-fetch sensitive (profiles/r01_*).
+__device__ __noinline__ void rnea_lane(const Smem& s, bool is_bias, int unit, float gz, float kl, float ka,
+                                       float* tau) {  // tau: 9 floats in shared memory, private to this lane
   constexpr bool kBias = true;  // the velocity terms are evaluated by every sweep (zeros for the unit sweeps)
   float w[3] = {0, 0, 0}, al[3] = {0, 0, 0}, a[3] = {0, 0, -gz}, vo[3] = {0, 0, 0};
-  float w6[3], al6[3], a6[3], vo6[3];
-#pragma unroll
+  float w6[3] = {0, 0, 0}, al6[3] = {0, 0, 0}, a6[3] = {0, 0, 0}, vo6[3] = {0, 0, 0};
   for (int j = 0; j < NL; ++j) tau[j] = 0.f;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < NL; ++i) {
     const int pa = parent_of(i);
     if (i == 7 || i == 8) {  // fingers hang off link 6
@@ -237,20 +252,18 @@ __device__ __forceinline__ void rnea_lane(const Smem& s, bool is_bias, int unit,
         N[0] += t[0] + kk * Iw[0]; N[1] += t[1] + kk * Iw[1]; N[2] += t[2] + kk * Iw[2];
       }
     }
-#pragma unroll
-    for (int j = 0; j < NL; ++j) {
-      if (is_ancestor_or_self(j, i)) {
-        float r[3] = {s.c[i][0] - s.p[j][0], s.c[i][1] - s.p[j][1], s.c[i][2] - s.p[j][2]};
-        cross3(t, r, F);
-        tau[j] += s.z[j][0] * (N[0] + t[0]) + s.z[j][1] * (N[1] + t[1]) + s.z[j][2] * (N[2] + t[2]);
-      }
+#pragma unroll 1
+    for (int j = i; j >= 0; j = parent_of(j)) {  // every joint on the path base -> link i feels link i's wrench
+      float r[3] = {s.c[i][0] - s.p[j][0], s.c[i][1] - s.p[j][1], s.c[i][2] - s.p[j][2]};
+      cross3(t, r, F);
+      tau[j] += s.z[j][0] * (N[0] + t[0]) + s.z[j][1] * (N[1] + t[1]) + s.z[j][2] * (N[2] + t[2]);
     }
   }
 }
 
 // Cholesky of the 9x9 SPD matrix in s.L (lower, in place); lanes cooperate per column.
-__device__ void chol9(float* Lm, int lane) {
-#pragma unroll
+__device__ __noinline__ void chol9(float* Lm, int lane) {
+#pragma unroll 1
   for (int j = 0; j < NL; ++j) {
     float d = 0.f;
     if (lane == 0) {
@@ -288,7 +301,7 @@ __device__ __forceinline__ void chol9_solve(const float* Lm, const float* b, flo
 }
 
 // ---- inverse kinematics (BussIK DLS restated, see oracle solve_ik) ------------------------------
-__device__ void solve_ik(Smem& s, const float* target, int lane) {
+__device__ __noinline__ void solve_ik(Smem& s, const float* target, int lane) {
   if (lane < NL) s.qik[lane] = s.q[lane];
   __syncwarp();
   const int iters = (int)P(s, MP_IK_ITERS);
@@ -312,15 +325,15 @@ __device__ void solve_ik(Smem& s, const float* target, int lane) {
     }
     if (lane < NL) {
 #pragma unroll
-      for (int j = 0; j < NL; ++j) s.A[lane * NL + j] = Arow[j];
-      s.b[lane] = Jc[0] * e[0] + Jc[1] * e[1] + Jc[2] * e[2];
+      for (int j = 0; j < NL; ++j) s.ik.A[lane * NL + j] = Arow[j];
+      s.ik.b[lane] = Jc[0] * e[0] + Jc[1] * e[1] + Jc[2] * e[2];
     }
     __syncwarp();
-    chol9(s.A, lane);
+    chol9(s.ik.A, lane);
     float bb[NL], x[NL];
 #pragma unroll
-    for (int j = 0; j < NL; ++j) bb[j] = s.b[j];
-    chol9_solve(s.A, bb, x);  // every lane solves the same system (cheap, avoids a broadcast)
+    for (int j = 0; j < NL; ++j) bb[j] = s.ik.b[j];
+    chol9_solve(s.ik.A, bb, x);  // every lane solves the same system (cheap, avoids a broadcast)
     float mx = 0.f;
 #pragma unroll
     for (int j = 0; j < NL; ++j) mx = fmaxf(mx, fabsf(x[j]));
@@ -382,8 +395,8 @@ __device__ __forceinline__ void push_contacts(Smem& s, unsigned mask, int lane, 
   __syncwarp();
 }
 
-__device__ void find_contacts(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, float block_margin,
-                              int lane) {
+__device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
+                                           float block_margin, int lane) {
   if (lane == 0) { s.nc = 0; s.na = 0; }
   // block frame
   if (lane == 0) {
@@ -496,11 +509,10 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   const float dt = P(s, MP_DT), gz = P(s, MP_GRAVITY), kl = P(s, MP_LIN_DAMP), ka = P(s, MP_ANG_DAMP);
   fk(s, s.q, lane);
   {  // mass matrix columns (lanes 0..8) and bias (lane 9)
-    float tau[NL];
     if (lane <= NL) {  // one code path for all ten sweeps (no divergence): unit lanes see zero velocity / gravity
       const bool is_bias = lane == NL;
+      float* tau = s.tauw[lane];
       rnea_lane(s, is_bias, lane, is_bias ? gz : 0.f, is_bias ? kl : 0.f, is_bias ? ka : 0.f, tau);
-#pragma unroll
       for (int i = 0; i < NL; ++i) {
         if (is_bias) s.bias[i] = tau[i];
         else s.L[i * NL + lane] = tau[i];
@@ -611,37 +623,33 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
         for (int a = 0; a < 3; ++a) { J[9 + a] = dir[a]; J[12 + a] = t[a]; }
       }
       float Wv[NU];
-#pragma unroll
-      for (int i = 0; i < NL; ++i) Wv[i] = 0.f;
-      if (link >= 0) {
+      float diag = 0.f, rel = 0.f;
+      if (link >= 0) {  // arm part, compact runtime loops through this row's shared-memory slot
         const float sgn = hasb ? -1.f : 1.f;
-#pragma unroll
-        for (int j = 0; j < NL; ++j) {
-          // joint j moves `link` iff it lies on the path base -> link
-          const bool on = (j <= 6) ? (link >= j) : (link == j);
-          if (on) {
-            float r[3] = {x[0] - s.p[j][0], x[1] - s.p[j][1], x[2] - s.p[j][2]}, cr[3];
-            cross3(cr, s.z[j], r);
-            J[j] = sgn * dot3(dir, cr);
-          }
+        const int as = s.carm[ci] * 3 + kind;
+        float* Jr = s.Ja[as];
+        float* Wr = s.Wa[as];
+        for (int j = 0; j < NL; ++j) Jr[j] = 0.f;
+#pragma unroll 1
+        for (int j = link; j >= 0; j = parent_of(j)) {  // joints on the path base -> link
+          float r[3] = {x[0] - s.p[j][0], x[1] - s.p[j][1], x[2] - s.p[j][2]}, cr[3];
+          cross3(cr, s.z[j], r);
+          Jr[j] = sgn * dot3(dir, cr);
         }
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < NL; ++i) {
           float acc = 0.f;
-#pragma unroll
-          for (int j = 0; j < NL; ++j) acc += s.Minv[i * NL + j] * J[j];
-          Wv[i] = acc;
+          for (int j = 0; j < NL; ++j) acc += s.Minv[i * NL + j] * Jr[j];
+          Wr[i] = acc;
+          diag += Jr[i] * acc;
+          rel += Jr[i] * s.u[i];
         }
-        const int as = s.carm[ci] * 3 + kind;
-#pragma unroll
-        for (int i = 0; i < NL; ++i) { s.Ja[as][i] = J[i]; s.Wa[as][i] = Wv[i]; }
       }
 #pragma unroll
       for (int a = 0; a < 3; ++a) Wv[9 + a] = J[9 + a] / ep.bmass;
       mat_vec(Wv + 12, s.Ibinv, J + 12);
-      float diag = 0.f, rel = 0.f;
 #pragma unroll
-      for (int a = 0; a < NU; ++a) { diag += J[a] * Wv[a]; rel += J[a] * s.u[a]; }
+      for (int a = 9; a < NU; ++a) { diag += J[a] * Wv[a]; rel += J[a] * s.u[a]; }
       const float invd = 1.f / diag;
       float rhs;
       if (kind == 0) {
@@ -863,18 +871,48 @@ __device__ __forceinline__ void store_state(const Smem& s, float* __restrict__ s
   }
 }
 
+__device__ __forceinline__ float goal_dist(const Smem& s) {
+  const float dx = s.bp[0] - s.goal[0], dy = s.bp[1] - s.goal[1], dz = s.bp[2] - s.goal[2];
+  return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
+__device__ void env_step_core(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, const float* a_in, int lane);
+
 // ---- kernels ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 16) env_step_kernel(const float* __restrict__ model_g, EnvParams ep,
-                                                      float* __restrict__ state, const float* __restrict__ actions,
-                                                      float* __restrict__ obs, float* __restrict__ ag,
-                                                      float* __restrict__ reward, float* __restrict__ success) {
-  __shared__ Smem s;
-  const int e = blockIdx.x, lane = threadIdx.x;
-  stage_model(s, model_g, lane);
+__global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
+env_step_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, float* __restrict__ state,
+                const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ ag,
+                float* __restrict__ reward, float* __restrict__ success) {
+  __shared__ __align__(16) float model_s[STAGED];
+  __shared__ unsigned long long mbar_s;
+  __shared__ Smem sw[WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * WARPS + warp;
+  stage_model(model_s, &mbar_s, model_g, threadIdx.x);
+  if (e >= n_envs) return;  // whole warp
+  Smem& s = sw[warp];
+  if (lane == 0) s.model = model_s;
+  __syncwarp();
   load_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
   float a[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) a[i] = fminf(fmaxf(actions[e * 4 + i], -0.5f), 0.5f);
+  for (int i = 0; i < 4; ++i) a[i] = actions[e * 4 + i];
+  env_step_core(s, ep, model_g, a, lane);
+  observe(s, lane, obs + (size_t)e * BMI_OBS_DIM, ag + (size_t)e * BMI_GOAL_DIM);
+  if (lane == 0) {
+    const float dist = goal_dist(s);
+    const float thr = P(s, MP_DIST_THRESHOLD);
+    if (success) success[e] = dist < thr ? 1.f : 0.f;
+    if (reward) reward[e] = dist > thr ? -1.f : -0.f;
+  }
+  store_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
+}
+
+// clip, (pick: auto-grip), IK, motor set-points, n_substeps sub-steps  (bmirobot_env_push_F.py:92-101)
+__device__ __noinline__ void env_step_core(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
+                                           const float* a_in, int lane) {
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = fminf(fmaxf(a_in[i], -0.5f), 0.5f);
   if (ep.task == BMI_TASK_PUSH) a[3] = 0.f;  // bmirobot_env_push_F.py:94
   fk(s, s.q, lane);
   if (ep.task == BMI_TASK_PICK) {  // auto-grip (bmirobot_env_pickandplace_v2.py:94-95)
@@ -894,24 +932,182 @@ __global__ void __launch_bounds__(32, 16) env_step_kernel(const float* __restric
   __syncwarp();
   const int nsub = (int)P(s, MP_N_SUBSTEPS);
   for (int i = 0; i < nsub; ++i) substep(s, ep, model_g, lane);
-  observe(s, lane, obs + (size_t)e * BMI_OBS_DIM, ag + (size_t)e * BMI_GOAL_DIM);
-  if (lane == 0) {
-    const float dx = s.bp[0] - s.goal[0], dy = s.bp[1] - s.goal[1], dz = s.bp[2] - s.goal[2];
-    const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-    const float thr = P(s, MP_DIST_THRESHOLD);
-    if (success) success[e] = dist < thr ? 1.f : 0.f;
-    if (reward) reward[e] = dist > thr ? -1.f : -0.f;
-  }
-  store_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
 }
 
-__global__ void __launch_bounds__(32) env_reset_kernel(const float* __restrict__ model_g, float* __restrict__ state,
-                                                       const unsigned char* __restrict__ mask,
-                                                       const float* __restrict__ init, float* __restrict__ obs,
-                                                       float* __restrict__ ag, float* __restrict__ g) {
-  __shared__ Smem s;
-  const int e = blockIdx.x, lane = threadIdx.x;
-  stage_model(s, model_g, lane);
+// ---- fused rollout: policy MLP + exploration noise + episode record + env step, T steps per launch ---------------
+struct RolloutArgs {
+  int T, explore;
+  const float* actor_t;      // transposed actor weights: Wt1[Dx][HID] b1 Wt2[HID][HID] b2 Wt3[HID][HID] b3 Wt4[HID][4] b4
+  const float *o_mean, *o_std, *g_mean, *g_std;
+  float clip_range, action_max, noise_eps, random_eps, late_clip;
+  unsigned long long seed;
+  const unsigned long long* counter;
+  float *ep_obs, *ep_ag, *ep_g, *ep_act;   // [n][T+1][27] [n][T+1][3] [n][T][3] [n][T][4] or null
+  const float* init;                       // [n][8] placements: the episode starts with a reset
+  float *obs, *ag, *g, *success;           // final observation / flags
+};
+
+// one hidden layer: out[HID] = relu(Wt[n_in][HID]^T x + b); lane owns outputs 8*lane .. 8*lane+7
+__device__ __forceinline__ void policy_layer(const float* __restrict__ Wt, const float* __restrict__ b, const float* x,
+                                             int n_in, float* out, int lane) {
+  float acc[8];
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * lane), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * lane + 1);
+  acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  const float4* W4 = reinterpret_cast<const float4*>(Wt) + 2 * lane;
+#pragma unroll 4
+  for (int k = 0; k < n_in; ++k) {
+    const float xk = x[k];
+    const float4 w0 = __ldg(W4 + (size_t)k * (HID / 4)), w1 = __ldg(W4 + (size_t)k * (HID / 4) + 1);
+    acc[0] = fmaf(xk, w0.x, acc[0]); acc[1] = fmaf(xk, w0.y, acc[1]); acc[2] = fmaf(xk, w0.z, acc[2]); acc[3] = fmaf(xk, w0.w, acc[3]);
+    acc[4] = fmaf(xk, w1.x, acc[4]); acc[5] = fmaf(xk, w1.y, acc[5]); acc[6] = fmaf(xk, w1.z, acc[6]); acc[7] = fmaf(xk, w1.w, acc[7]);
+  }
+  float4* o4 = reinterpret_cast<float4*>(out) + 2 * lane;
+  o4[0] = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+  o4[1] = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+  __syncwarp();
+}
+
+__device__ __forceinline__ float norm_clip(float v, float m, float sd, float clip) {
+  // ddpg_agent._preproc_inputs: float64 (v - mean) / std, clip, then float32 (same as bmi_preproc_inputs)
+  const double z = __ddiv_rn(__dsub_rn((double)v, (double)m), (double)sd);
+  return (float)fmin(fmax(z, -(double)clip), (double)clip);
+}
+
+__global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
+rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, float* __restrict__ state, RolloutArgs ra) {
+  __shared__ __align__(16) float model_s[STAGED];
+  __shared__ unsigned long long mbar_s;
+  __shared__ Smem sw[WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * WARPS + warp;
+  stage_model(model_s, &mbar_s, model_g, threadIdx.x);
+  if (e >= n_envs) return;
+  Smem& s = sw[warp];
+  if (lane == 0) s.model = model_s;
+  __syncwarp();
+  float* st = state + (size_t)e * BMI_ENV_STATE_DIM;
+  if (ra.init != nullptr) {  // reset (bmirobot_env_push_F.py:110-165)
+    const float* in = ra.init + (size_t)e * 8;
+    for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {
+      float v = 0.f;
+      if (i >= ST_BPOS && i < ST_BPOS + 3) v = in[i - ST_BPOS];
+      else if (i == ST_BQUAT + 2) v = sinf(0.5f * in[3]);
+      else if (i == ST_BQUAT + 3) v = cosf(0.5f * in[3]);
+      else if (i >= ST_GOAL && i < ST_GOAL + 3) v = in[4 + i - ST_GOAL];
+      st[i] = v;
+    }
+    __syncwarp();
+  }
+  load_state(s, st, lane);
+  observe(s, lane, s.obs, s.obs + BMI_OBS_DIM);
+  constexpr int Do = BMI_OBS_DIM, Dg = BMI_GOAL_DIM, Da = BMI_ACT_DIM, Dx = Do + Dg;
+  const float* Wt1 = ra.actor_t;
+  const float* b1 = Wt1 + Dx * HID;
+  const float* Wt2 = b1 + HID;
+  const float* b2 = Wt2 + HID * HID;
+  const float* Wt3 = b2 + HID;
+  const float* b3 = Wt3 + HID * HID;
+  const float* Wt4 = b3 + HID;
+  const float* b4 = Wt4 + HID * Da;
+  const unsigned long long ctr0 = ra.explore ? *ra.counter : 0ull;
+  for (int t = 0; t < ra.T; ++t) {
+    // ---- record obs / ag / g of step t -----------------------------------------------------------------
+    if (ra.ep_obs) {
+      if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + t) * Do + lane] = s.obs[lane];
+      if (lane < Dg) {
+        ra.ep_ag[((size_t)e * (ra.T + 1) + t) * Dg + lane] = s.obs[Do + lane];
+        ra.ep_g[((size_t)e * ra.T + t) * Dg + lane] = s.goal[lane];
+      }
+    }
+    // ---- policy: normalise -> 3 hidden layers -> tanh head (ddpg_agent.py:113-116) ------------------------
+    if (lane < Do) s.pol.x[lane] = norm_clip(s.obs[lane], ra.o_mean[lane], ra.o_std[lane], ra.clip_range);
+    else if (lane < Dx) s.pol.x[lane] = norm_clip(s.goal[lane - Do], ra.g_mean[lane - Do], ra.g_std[lane - Do], ra.clip_range);
+    __syncwarp();
+    policy_layer(Wt1, b1, s.pol.x, Dx, s.pol.hA, lane);
+    policy_layer(Wt2, b2, s.pol.hA, HID, s.pol.hB, lane);
+    policy_layer(Wt3, b3, s.pol.hB, HID, s.pol.hA, lane);
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = lane * 8 + kk;
+      const float hk = s.pol.hA[k];
+      const float4 w = __ldg(reinterpret_cast<const float4*>(Wt4) + k);
+      z[0] = fmaf(hk, w.x, z[0]); z[1] = fmaf(hk, w.y, z[1]); z[2] = fmaf(hk, w.z, z[2]); z[3] = fmaf(hk, w.w, z[3]);
+    }
+    float a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = z[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      a[j] = ra.action_max * tanhf(v + __ldg(b4 + j));
+    }
+    if (ra.explore) {  // _select_actions (ddpg_agent.py:174-184): same Philox stream as bmi_select_actions
+      const unsigned long long c = ctr0 + (unsigned long long)t * (unsigned long long)n_envs + (unsigned long long)e;
+      const Philox4 pg = philox4x32_10(ra.seed, 3 * c, kStreamExplore);
+      const Philox4 pu = philox4x32_10(ra.seed, 3 * c + 1, kStreamExplore);
+      const Philox4 pb = philox4x32_10(ra.seed, 3 * c + 2, kStreamExplore);
+      const bool take_random = u24(pb.v[0]) < ra.random_eps;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pair = (j >> 1) & 1;
+        const float u1 = 1.0f - u24(pg.v[2 * pair]);
+        const float u2 = u24(pg.v[2 * pair + 1]);
+        const float rad = sqrtf(-2.0f * logf(u1));
+        const float gz = (j & 1) ? rad * sinf(6.28318530717958647692f * u2) : rad * cosf(6.28318530717958647692f * u2);
+        float v = a[j] + ra.noise_eps * ra.action_max * gz;
+        v = fminf(fmaxf(v, -ra.action_max), ra.action_max);
+        const float rv = -ra.action_max + 2.0f * ra.action_max * u24(pu.v[j & 3]);
+        if (take_random) v = rv;
+        if (ra.late_clip > 0.f) v = fminf(fmaxf(v, -ra.late_clip), ra.late_clip);
+        a[j] = v;
+      }
+    }
+    if (ra.ep_act && lane < Da) {
+      float v = a[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) if (lane == j) v = a[j];
+      ra.ep_act[((size_t)e * ra.T + t) * Da + lane] = v;
+    }
+    __syncwarp();
+    // ---- env step -------------------------------------------------------------------------------------------
+    env_step_core(s, ep, model_g, a, lane);
+    observe(s, lane, s.obs, s.obs + Do);
+  }
+  if (ra.ep_obs) {
+    if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + ra.T) * Do + lane] = s.obs[lane];
+    if (lane < Dg) ra.ep_ag[((size_t)e * (ra.T + 1) + ra.T) * Dg + lane] = s.obs[Do + lane];
+  }
+  if (ra.obs && lane < Do) ra.obs[(size_t)e * Do + lane] = s.obs[lane];
+  if (ra.ag && lane < Dg) ra.ag[(size_t)e * Dg + lane] = s.obs[Do + lane];
+  if (ra.g && lane < Dg) ra.g[(size_t)e * Dg + lane] = s.goal[lane];
+  if (ra.success && lane == 0) ra.success[e] = goal_dist(s) < P(s, MP_DIST_THRESHOLD) ? 1.f : 0.f;
+  store_state(s, st, lane);
+}
+
+// W[out][in] (torch layout) -> Wt[in][out]
+__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int n_out, int n_in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_out * n_in) {
+    const int o = i / n_in, k = i % n_in;
+    Wt[(size_t)k * n_out + o] = W[i];
+  }
+}
+
+__global__ void __launch_bounds__(32 * WARPS)
+env_reset_kernel(const float* __restrict__ model_g, int n_envs, float* __restrict__ state,
+                 const unsigned char* __restrict__ mask, const float* __restrict__ init, float* __restrict__ obs,
+                 float* __restrict__ ag, float* __restrict__ g) {
+  __shared__ __align__(16) float model_s[STAGED];
+  __shared__ unsigned long long mbar_s;
+  __shared__ Smem sw[WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * WARPS + warp;
+  stage_model(model_s, &mbar_s, model_g, threadIdx.x);
+  if (e >= n_envs) return;
+  Smem& s = sw[warp];
+  if (lane == 0) s.model = model_s;
+  __syncwarp();
   float* st = state + (size_t)e * BMI_ENV_STATE_DIM;
   if (mask == nullptr || mask[e]) {
     const float* in = init + (size_t)e * 8;
@@ -1030,7 +1226,8 @@ extern "C" int32_t bmi_env_num_envs(const bmi_env* h) { return h ? h->n_envs : -
 extern "C" int bmi_env_reset(bmi_env* h, const uint8_t* mask, const float* init, float* obs, float* ag, float* g,
                              bmi_stream_t stream) {
   BMI_REQUIRE(h && init && obs && ag && g, "bmi_env_reset: null pointer");
-  env_reset_kernel<<<h->n_envs, 32, 0, as_stream(stream)>>>(h->model_dev, h->state_dev, mask, init, obs, ag, g);
+  env_reset_kernel<<<(h->n_envs + WARPS - 1) / WARPS, 32 * WARPS, 0, as_stream(stream)>>>(h->model_dev, h->n_envs, h->state_dev, mask,
+                                                                                           init, obs, ag, g);
   BMI_LAUNCHED();
   return BMI_OK;
 }
@@ -1047,7 +1244,8 @@ extern "C" int bmi_env_sample_init(bmi_env* h, uint64_t seed, uint64_t* counter,
 extern "C" int bmi_env_step(bmi_env* h, const float* actions, float* obs, float* ag, float* reward, float* success,
                             bmi_stream_t stream) {
   BMI_REQUIRE(h && actions && obs && ag, "bmi_env_step: null pointer");
-  env_step_kernel<<<h->n_envs, 32, 0, as_stream(stream)>>>(h->model_dev, h->ep, h->state_dev, actions, obs, ag, reward, success);
+  env_step_kernel<<<(h->n_envs + WARPS - 1) / WARPS, 32 * WARPS, 0, as_stream(stream)>>>(h->model_dev, h->ep, h->n_envs, h->state_dev,
+                                                                                          actions, obs, ag, reward, success);
   BMI_LAUNCHED();
   return BMI_OK;
 }
@@ -1065,5 +1263,52 @@ extern "C" int bmi_env_set_state(bmi_env* h, const float* st, bmi_stream_t strea
   const int n = h->n_envs * BMI_ENV_STATE_DIM;
   copy_state_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(h->state_dev, st, n);
   BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_actor_transpose(const float* actor_params, int32_t obs_dim, int32_t goal_dim, int32_t act_dim,
+                                   int32_t hidden, float* actor_t, bmi_stream_t stream) {
+  BMI_REQUIRE(actor_params && actor_t, "bmi_actor_transpose: null pointer");
+  BMI_REQUIRE(hidden == HID && obs_dim == BMI_OBS_DIM && goal_dim == BMI_GOAL_DIM && act_dim == BMI_ACT_DIM,
+              "bmi_actor_transpose: the fused rollout is compiled for 27+3 -> 256 -> 256 -> 256 -> 4");
+  cudaStream_t st = as_stream(stream);
+  const int ins[4] = {obs_dim + goal_dim, hidden, hidden, hidden}, outs[4] = {hidden, hidden, hidden, act_dim};
+  size_t off = 0;
+  for (int l = 0; l < 4; ++l) {
+    const int n = ins[l] * outs[l];
+    transpose_kernel<<<(n + 255) / 256, 256, 0, st>>>(actor_params + off, actor_t + off, outs[l], ins[l]);
+    BMI_LAUNCHED();
+    off += n;
+    BMI_CUDA_CHECK(cudaMemcpyAsync(actor_t + off, actor_params + off, outs[l] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    off += outs[l];
+  }
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream_t stream) {
+  BMI_REQUIRE(h && a, "bmi_env_rollout: null pointer");
+  BMI_REQUIRE(a->T > 0 && a->actor_t && a->o_mean && a->o_std && a->g_mean && a->g_std, "bmi_env_rollout: missing policy inputs");
+  BMI_REQUIRE(!a->explore || a->counter, "bmi_env_rollout: exploration needs a Philox counter");
+  RolloutArgs ra;
+  ra.T = a->T; ra.explore = a->explore; ra.actor_t = a->actor_t;
+  ra.o_mean = a->o_mean; ra.o_std = a->o_std; ra.g_mean = a->g_mean; ra.g_std = a->g_std;
+  ra.clip_range = a->clip_range; ra.action_max = a->action_max; ra.noise_eps = a->noise_eps;
+  ra.random_eps = a->random_eps; ra.late_clip = a->late_clip; ra.seed = a->seed; ra.counter = (const unsigned long long*)a->counter;
+  ra.ep_obs = ra.ep_ag = ra.ep_g = ra.ep_act = nullptr;
+  if (a->episodes) {
+    const bmi_episodes* e = a->episodes;
+    BMI_REQUIRE(e->dtype == BMI_F32 && e->T == a->T && e->n_episodes == h->n_envs && e->obs_dim == BMI_OBS_DIM &&
+                    e->goal_dim == BMI_GOAL_DIM && e->act_dim == BMI_ACT_DIM,
+                "bmi_env_rollout: episodes must be float32 [n_envs][T(+1)][27|3|3|4]");
+    ra.ep_obs = (float*)e->obs; ra.ep_ag = (float*)e->ag; ra.ep_g = (float*)e->g; ra.ep_act = (float*)e->actions;
+  }
+  ra.init = a->init; ra.obs = a->obs; ra.ag = a->ag; ra.g = a->g; ra.success = a->success;
+  cudaStream_t st = as_stream(stream);
+  rollout_kernel<<<(h->n_envs + WARPS - 1) / WARPS, 32 * WARPS, 0, st>>>(h->model_dev, h->ep, h->n_envs, h->state_dev, ra);
+  BMI_LAUNCHED();
+  if (a->explore) {
+    advance_counter_kernel3<<<1, 1, 0, st>>>(a->counter, (uint64_t)a->T * (uint64_t)h->n_envs);
+    BMI_LAUNCHED();
+  }
   return BMI_OK;
 }

@@ -81,6 +81,7 @@ class ddpg_agent:
         self._losses = f32(2)
         self._draw = (torch.zeros(B, dtype=torch.int64, device=self.device), torch.zeros(B, dtype=torch.int64, device=self.device),
                       torch.zeros(B, dtype=torch.float64, device=self.device), torch.zeros(B, dtype=torch.float64, device=self.device))
+        self._actor_t = torch.zeros_like(self.actor_network.flat)   # transposed copy read by the fused rollout
         self._ctr_her = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._ctr_explore = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._seed = int(args.seed) + utils.rank()
@@ -170,10 +171,23 @@ class ddpg_agent:
             return   # the warm-up already did this call's work
         g.replay()
 
+    def _fused_rollout_body(self, explore, late_clip):
+        p = self.env_params
+        _lib.call("bmi_actor_transpose", _lib.ptr(self.actor_network.flat), p['obs'], p['goal'], p['action'], 256,
+                  _lib.ptr(self._actor_t), _lib.stream_ptr())
+        self.vec.rollout(self.T, self._actor_t, self.o_norm, self.g_norm, self.args.clip_range, explore,
+                         noise_eps=self.args.noise_eps, random_eps=self.args.random_eps, late_clip=late_clip,
+                         seed=self._seed, counter=self._ctr_explore, episodes=self.ep if explore else None)
+
     def rollout(self, epoch=0):
-        """One batch of R simultaneous episodes (ddpg_agent.py:103-141); fills self.ep."""
+        """One batch of R simultaneous episodes (ddpg_agent.py:103-141); fills self.ep.  Default: the fused
+        per-env rollout kernel (one launch per episode batch); args.fused_rollout=False runs the step-wise
+        pipeline (cuBLASLt actor + one env kernel per step) inside a CUDA graph."""
         late = 0.15 if epoch >= getattr(self.args, "late_clip_epoch", 100) else 0.0
-        self._run_graphed(("rollout", late), lambda: self._rollout_body(late))
+        if getattr(self.args, "fused_rollout", True):
+            self._fused_rollout_body(True, late)
+        else:
+            self._run_graphed(("rollout", late), lambda: self._rollout_body(late))
         self.env_steps += self.R * self.T
 
     # ---- normaliser ------------------------------------------------------------------------------------
@@ -317,7 +331,10 @@ class ddpg_agent:
         n_batches = max(1, -(-int(self.args.n_test_rollouts) // self.R))
         total = torch.zeros((), dtype=torch.float32, device=self.device)
         for _ in range(n_batches):
-            self._run_graphed(("eval",), self._eval_body)
+            if getattr(self.args, "fused_rollout", True):
+                self._fused_rollout_body(False, 0.0)
+            else:
+                self._run_graphed(("eval",), self._eval_body)
             total += self.vec.success.mean()
         local = torch.stack([total / n_batches]).contiguous()
         utils.allreduce_sum_(local)

@@ -95,3 +95,36 @@ def test_demo_buffer_preload(tmp_path, golden_dir):
     assert ag.buffer.current_size == d["obs"].shape[0]
     assert np.allclose(ag.buffer.buffers['obs'][:2].cpu().numpy(), d["obs"][:2].astype(np.float32))
     assert float(ag.o_norm.total_count[0]) == 1.0     # normalisers are NOT updated from demos (ddpg_agent.py:49-53)
+
+
+def test_fused_rollout_matches_stepwise_pipeline(tmp_path):
+    """The fused per-env rollout kernel (policy MLP in-kernel) against the step-wise pipeline (cuBLASLt actor +
+    one env kernel per step): same Philox noise, same physics; only the MLP's fp32 summation order differs."""
+    ag1, _ = _agent(tmp_path, n_envs=64, fused_rollout=True)
+    ag2, _ = _agent(tmp_path, n_envs=64, fused_rollout=False, use_cuda_graphs=False)
+    ag2.actor_network.flat.copy_(ag1.actor_network.flat)
+    # non-trivial normaliser statistics
+    for ag in (ag1, ag2):
+        g = torch.Generator(device="cuda").manual_seed(0)
+        ag.o_norm.update(torch.randn(200, 27, device="cuda", generator=g) * 0.3)
+        ag.g_norm.update(0.3 + torch.randn(200, 3, device="cuda", generator=g) * 0.1)
+        ag.o_norm.recompute_stats()
+        ag.g_norm.recompute_stats()
+    ag1.rollout(0)
+    ag2.rollout(0)
+    torch.cuda.synchronize()
+    e1, e2 = ag1.ep, ag2.ep
+    assert torch.equal(e1['obs'][:, 0], e2['obs'][:, 0]) and torch.equal(e1['g'], e2['g'])     # same reset
+    assert (e1['actions'][:, 0] - e2['actions'][:, 0]).abs().max() < 1e-5                      # same policy + noise
+    # random (epsilon) actions are bit-identical whatever the MLP rounding
+    big = e2['actions'].abs().amax(dim=2) > 0.05
+    assert big.float().mean() > 0.2
+    d1 = (e1['obs'][:, 1, :3] - e2['obs'][:, 1, :3]).abs().max()
+    assert d1 < 1e-4, d1
+    # trajectories stay statistically aligned early on (contacts make them diverge later)
+    med = (e1['obs'][:, 10, :3] - e2['obs'][:, 10, :3]).abs().amax(dim=1).median()
+    assert med < 5e-3, med
+    assert torch.equal(e1['ag'], e1['obs'][:, :, 12:15]) and e1['actions'].abs().max() <= 0.5
+    assert torch.isfinite(e1['obs']).all()
+    # evaluation path runs and reports a rate
+    assert 0.0 <= ag1._eval_agent() <= 1.0
