@@ -297,7 +297,8 @@ def run_gpu(args):
                              "note": "FP32-issue/latency-bound kernel: the HBM fraction is small by construction (SURVEY 8d)"},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps),
                 "clocks": sampler.summary()}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    agent.release_graphs()
     utils.shutdown_comm()
 
 

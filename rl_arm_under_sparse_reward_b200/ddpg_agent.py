@@ -285,6 +285,11 @@ class ddpg_agent:
         self._run_graphed(("update", n), body)
         self.updates += n
 
+    def release_graphs(self):
+        """Drop the captured CUDA graphs (they hold references to the NCCL communicator)."""
+        torch.cuda.synchronize()
+        self._graphs.clear()
+
     def losses(self):
         return self._losses.cpu().numpy().copy()
 

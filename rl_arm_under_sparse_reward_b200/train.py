@@ -34,6 +34,7 @@ def launch(args):
     trainer = ddpg_agent(args, env, env_params)
     trainer.learn()
     trainer.plot_success_rate()
+    trainer.release_graphs()
     utils.shutdown_comm()
     return trainer
 

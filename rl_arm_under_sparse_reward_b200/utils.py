@@ -54,6 +54,10 @@ def init_comm(backend=None):
 
 
 def shutdown_comm():
+    """Tear the communicators down.  CUDA graphs that captured NCCL operations keep the communicator busy:
+    release them first (``ddpg_agent.release_graphs()``), otherwise ncclCommDestroy waits for ever."""
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     if _state["comm"] is not None:
         _lib.call("bmi_comm_destroy", _state["comm"])
         _state["comm"] = None
