@@ -669,31 +669,25 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   }
   __syncwarp();
   // ---- projected Gauss-Seidel ---------------------------------------------------------------------------
-  // Velocity deltas: lane j < 9 owns the arm's dv[j]; the block's six deltas are REPLICATED in every lane
-  // (dvb), so block-only rows (block on table: the common case) need no cross-lane traffic at all.
-  // Motor rows (always 9, J = e_j) live in registers: lane j owns row j's rhs / 1/diag / lambda and every lane
-  // keeps its row of M^-1 (mrow[j] = Minv[lane][j]); one shuffle per motor row broadcasts the impulse.
+  // The solve is a strictly sequential chain (row r needs row r-1's update): what bounds an env with many active
+  // rows is the latency of one row, and — when few warps are left on an SM — the instruction fetch of the loop
+  // body, so the body is kept compact enough for the L0 instruction cache (no unrolling over rows; measured
+  // faster than register-resident unrolled motor rows and than fully replicated state, profiles/r01_*).
+  // State: lane j < 9 owns the arm's dv[j]; the block's six deltas are REPLICATED in every lane (dvb), so
+  // block-only rows (block on table: the common case) need no cross-lane traffic; rows that touch an arm link
+  // reduce their 9-term dot product with one 16-lane butterfly; motor / limit rows (J = +-e_j) need one shuffle.
   float dv = 0.f;
   float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float mrow[NL];
-#pragma unroll
-  for (int j = 0; j < NL; ++j) mrow[j] = lane < NL ? s.Minv[lane * NL + j] : 0.f;
-  const int ml = lane < NL ? lane : 0;
-  const float m_invd = s.invd[ml], m_diag = s.Minv[ml * NL + ml], m_rhs = s.rhs[ml];
-  float m_lam = 0.f;
-  float mdiag[NL];
-#pragma unroll
-  for (int j = 0; j < NL; ++j) mdiag[j] = __shfl_sync(FULL, m_diag, j);
   const bool arm_lane = lane < NL;
+  const int al = arm_lane ? lane : 0;
   const int max_it = (int)P(s, MP_SOLVER_ITERS);
   const float thresh = P(s, MP_RESIDUAL_THRESH);
-  // J_r . dv for contact row r of contact c (kind 0/1/2): block part from registers, arm part by shuffle-reduce
   auto row_dot = [&](const float4& r0, const float4& r1, int as_row) -> float {
-    float d0 = r0.x * dvb[0] + r0.y * dvb[1] + r0.z * dvb[2];
-    float d1 = r0.w * dvb[3] + r1.x * dvb[4] + r1.y * dvb[5];
+    const float d0 = r0.x * dvb[0] + r0.y * dvb[1] + r0.z * dvb[2];
+    const float d1 = r0.w * dvb[3] + r1.x * dvb[4] + r1.y * dvb[5];
     float dot = d0 + d1;
     if (as_row >= 0) {  // uniform branch
-      const float t = arm_lane ? s.Ja[as_row][lane] * dv : 0.f;
+      const float t = arm_lane ? s.Ja[as_row][al] * dv : 0.f;
       dot += __shfl_sync(FULL, warp_sum16(t), 0);
     }
     return dot;
@@ -701,35 +695,25 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   auto row_apply = [&](const float4& r1, const float4& r2, int as_row, float d) {
     dvb[0] = fmaf(r1.z, d, dvb[0]); dvb[1] = fmaf(r1.w, d, dvb[1]); dvb[2] = fmaf(r2.x, d, dvb[2]);
     dvb[3] = fmaf(r2.y, d, dvb[3]); dvb[4] = fmaf(r2.z, d, dvb[4]); dvb[5] = fmaf(r2.w, d, dvb[5]);
-    if (as_row >= 0 && arm_lane) dv = fmaf(s.Wa[as_row][lane], d, dv);
+    if (as_row >= 0 && arm_lane) dv = fmaf(s.Wa[as_row][al], d, dv);
   };
   for (int it = 0; it < max_it; ++it) {
     float resid = 0.f;
-#pragma unroll
-    for (int j = 0; j < NL; ++j) {  // motors
-      float d = m_rhs - dv * m_invd;                       // meaningful in lane j (its dv IS dv[j])
-      const float sum = fminf(fmaxf(m_lam + d, -max_imp), max_imp);
-      d = sum - m_lam;
-      if (lane == j) m_lam = sum;
-      const float dj = __shfl_sync(FULL, d, j);
-      dv = fmaf(mrow[j], dj, dv);
-      const float res = dj * mdiag[j];
-      resid = fmaxf(resid, res * res);
-    }
-    for (int r = NL; r < n_nc; ++r) {  // violated joint limits: J = +-e_j
+#pragma unroll 1
+    for (int r = 0; r < n_nc; ++r) {  // motors (rows 0..8, J = e_r) then violated joint limits (J = +-e_j)
       const int jj = s.ncj[r];
       const int j = abs(jj) - 1;
       const float sgn = jj > 0 ? 1.f : -1.f;
-      const float invd = s.invd[r];
-      float d = s.rhs[r] - sgn * __shfl_sync(FULL, dv, j) * invd;
+      float d = s.rhs[r] - sgn * __shfl_sync(FULL, dv, j) * s.invd[r];
       const float old = s.lamn[r];
-      float sum = fminf(fmaxf(old + d, s.lo[r]), s.hi[r]);
+      const float sum = fminf(fmaxf(old + d, s.lo[r]), s.hi[r]);
       d = sum - old;
       s.lamn[r] = sum;
-      if (arm_lane) dv += sgn * s.Minv[lane * NL + j] * d;
+      dv = fmaf(sgn * s.Minv[al * NL + j], arm_lane ? d : 0.f, dv);
       const float res = d * s.Minv[j * NL + j];
       resid = fmaxf(resid, res * res);
     }
+#pragma unroll 1
     for (int c = 0; c < nc; ++c) {  // contact normals
       const float4 r0 = s.rd[c][0], r1 = s.rd[c][1], r2 = s.rd[c][2], r3 = s.rd[c][3];
       const int as = s.carm[c];
@@ -743,6 +727,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
       const float res = d * r3.z;
       resid = fmaxf(resid, res * res);
     }
+#pragma unroll 1
     for (int c = 0; c < nc; ++c) {  // friction cones
       const int ra = nc + 2 * c, rb = ra + 1;
       const float4 a0 = s.rd[ra][0], a1 = s.rd[ra][1], a2 = s.rd[ra][2], a3 = s.rd[ra][3];
