@@ -74,6 +74,7 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
   float lam[3 * MAXC];
   float invd[MAXNC], rhs[MAXNC], lo[MAXNC], hi[MAXNC], lamn[MAXNC];  // non-contact rows
   int ncj[MAXNC];                 // joint index (+1, sign = direction) of each non-contact row
+  float mdiag[NL];                // diagonal of M^-1
   float qik[NL];
 };
 
@@ -570,6 +571,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
     const float w = s.Minv[lane * NL + lane];
     const float target = P(s, MP_MOTOR_KP) * (s.qt[lane] - s.q[lane]) / dt + (1.f - P(s, MP_MOTOR_KD)) * s.qd[lane];
     s.invd[lane] = 1.f / w;
+    s.mdiag[lane] = w;
     s.rhs[lane] = (target - s.u[lane]) / w;
     s.lo[lane] = -max_imp; s.hi[lane] = max_imp; s.lamn[lane] = 0.f;
     s.ncj[lane] = lane + 1;
@@ -700,7 +702,18 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   for (int it = 0; it < max_it; ++it) {
     float resid = 0.f;
 #pragma unroll 1
-    for (int r = 0; r < n_nc; ++r) {  // motors (rows 0..8, J = e_r) then violated joint limits (J = +-e_j)
+    for (int r = 0; r < NL; ++r) {  // motors: J = e_r, bounds +-max_imp; lane r owns dv[r]
+      float d = s.rhs[r] - __shfl_sync(FULL, dv, r) * s.invd[r];
+      const float old = s.lamn[r];
+      const float sum = fminf(fmaxf(old + d, -max_imp), max_imp);
+      d = sum - old;
+      s.lamn[r] = sum;
+      dv = fmaf(s.Minv[al * NL + r], arm_lane ? d : 0.f, dv);
+      const float res = d * s.mdiag[r];
+      resid = fmaxf(resid, res * res);
+    }
+#pragma unroll 1
+    for (int r = NL; r < n_nc; ++r) {  // violated joint limits: J = +-e_j
       const int jj = s.ncj[r];
       const int j = abs(jj) - 1;
       const float sgn = jj > 0 ? 1.f : -1.f;
@@ -710,7 +723,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
       d = sum - old;
       s.lamn[r] = sum;
       dv = fmaf(sgn * s.Minv[al * NL + j], arm_lane ? d : 0.f, dv);
-      const float res = d * s.Minv[j * NL + j];
+      const float res = d * s.mdiag[j];
       resid = fmaxf(resid, res * res);
     }
 #pragma unroll 1
