@@ -93,17 +93,32 @@ def _oracle_worker(args):
 
 
 def cpu_env_steps_per_s(steps_per_core, cores):
-    """The oracle port of the env step on `cores` host processes (independent envs, like the reference's
-    one-env-per-MPI-rank layout); returns aggregate env-steps/s."""
+    """A bounded sample of the cycle on the host: `cores` processes each run `steps_per_core` env-steps of the
+    oracle port (independent envs, like the reference's one-env-per-MPI-rank layout), then the torch-CPU
+    restatement of _update_network runs the proportional number of updates (40 per 409 600 env-steps).
+    Throughput = env-steps / (slowest worker + updates); process start-up is not timed."""
     import multiprocessing as mp
     from oracle import physics_oracle
     physics_oracle.build()
     ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
         res = pool.map(_oracle_worker, [(1000 + i, steps_per_core) for i in range(cores)])
-    wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
+    t_env = max(r[1] for r in res)
+    n_upd = max(1, int(round(total * 40.0 / (N_ENVS * T))))
+    import torch
+    from oracle import ddpg_oracle
+    torch.set_num_threads(cores)
+    L = ddpg_oracle.Learner()
+    g = torch.Generator().manual_seed(0)
+    x, xn = torch.randn(256, 30, generator=g), torch.randn(256, 30, generator=g)
+    act, r = torch.rand(256, 4, generator=g) - 0.5, -torch.ones(256, 1)
+    L.update(x, xn, act, r)                      # warm-up (autograd graph caches, allocator)
+    t0 = time.perf_counter()
+    for _ in range(n_upd):
+        L.update(x, xn, act, r)
+    t_upd = time.perf_counter() - t0
+    wall = t_env + t_upd
     return total / wall, total, wall
 
 
@@ -112,21 +127,23 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core = 150
+    per_core = 2000
     for _ in range(args.warmup):
-        cpu_env_steps_per_s(20, cores)
+        cpu_env_steps_per_s(50, cores)
     vals, t_ms = [], []
     for _ in range(args.steps):
         v, total, wall = cpu_env_steps_per_s(per_core, cores)
         vals.append(v)
         t_ms.append(wall * 1e3)
     value = float(np.mean(vals))
-    sample = "%d cores x %d env-steps of the C oracle port per step (independent envs, exploration-like actions)" % (cores, per_core)
+    sample = ("per step: %d processes x %d env-steps of the C oracle port (restated env step, NOT PyBullet: pybullet/gym/"
+              "mpi4py are not installable in this image) + the proportional DDPG updates on torch CPU" % (cores, per_core))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(t_ms)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "push task, bmirobot env step (IK + 20 sub-steps + obs) on host cores; restated oracle, NOT PyBullet "
-                                   "(pybullet/gym/mpi4py are not installable in this image)", "envs": cores},
+            "config": {"workload": "push task, one env per host core, cycle shape of the GPU arm (100-step episodes, 40 HER DDPG updates "
+                                   "of batch 256 per 409600 env-steps); bounded sample per step", "envs": cores,
+                       "updates_per_env_step": 40.0 / (N_ENVS * T)},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -281,7 +298,8 @@ def run_gpu(args):
         cores = os.cpu_count() or 1
         v, total, wall = cpu_env_steps_per_s(args.cpu_steps_per_core, cores)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-               "sample": "%d env-steps of the C oracle port (restated env step, NOT PyBullet) on %d processes in %.1f s" % (total, cores, wall)}
+               "sample": "%d env-steps of the C oracle port (restated env step, NOT PyBullet) on %d processes + proportional "
+                         "torch-CPU updates, %.1f s" % (total, cores, wall)}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -310,7 +328,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--buffer-episodes", type=int, default=65536)
-    ap.add_argument("--cpu-steps-per-core", type=int, default=600)
+    ap.add_argument("--cpu-steps-per-core", type=int, default=12000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stepwise", action="store_true", help="step-wise rollout pipeline instead of the fused kernel")
