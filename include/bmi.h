@@ -215,6 +215,18 @@ int bmi_ddpg_backward(bmi_ddpg* h, const float* x_dev, const float* x_next_dev,
 int bmi_ddpg_grad_buffer(bmi_ddpg* h, float** grads_dev, int64_t* n);
 /* both Adam steps (ddpg_agent.py:272,277; torch.optim.Adam defaults, bias-corrected). */
 int bmi_ddpg_adam_step(bmi_ddpg* h, bmi_stream_t stream);
+/* Fused gradient sum over ranks + both Adam steps through NVLink peer memory (one process per GPU on one node):
+ * replaces [bmi_comm_allreduce_sum_f32 -> bmi_ddpg_adam_step], i.e. sync_grads (utils.py:43-48, SUM) + the two
+ * optimiser steps (ddpg_agent.py:272,277), by ONE kernel that reads every rank's gradient buffer with peer loads,
+ * adds them in rank order and updates the local replica; two flag barriers in peer memory order it against the
+ * neighbours' backward passes.  Set-up: every rank calls bmi_ddpg_p2p_export (128 bytes: two cudaIpcMemHandle_t),
+ * the caller all-gathers them, then bmi_ddpg_p2p_attach(rank, world, world x 128 bytes).  world <= 8.
+ * bmi_ddpg_p2p_status reports whether a flag wait ever timed out (about one second; the kernel then proceeds
+ * instead of hanging the GPU, and the results must be discarded). */
+int bmi_ddpg_p2p_export(bmi_ddpg* h, void* handles128_host);
+int bmi_ddpg_p2p_attach(bmi_ddpg* h, int32_t rank, int32_t world, const void* all_handles_host);
+int bmi_ddpg_adam_step_p2p(bmi_ddpg* h, bmi_stream_t stream);
+int bmi_ddpg_p2p_status(bmi_ddpg* h, int32_t* timed_out);
 /* _soft_update_target_network for both nets (ddpg_agent.py:220-222). */
 int bmi_ddpg_soft_update(bmi_ddpg* h, bmi_stream_t stream);
 

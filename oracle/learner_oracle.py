@@ -86,8 +86,16 @@ class Normalizer:
 
     def update(self, v):
         v = np.asarray(v, dtype=np.float64).reshape(-1, self.size)
-        self.local_sum += v.sum(axis=0)
-        self.local_sumsq += np.square(v).sum(axis=0)
+        if v.shape[0] <= 1024:      # the reference's case (100 rows): numpy's own sequential row order
+            s, q = v.sum(axis=0), np.square(v).sum(axis=0)
+        else:                       # csrc/normalizer.cu norm_chunk_kernel: 1024-row chunks, chunk sums added in order
+            chunks = [v[i:i + 1024] for i in range(0, v.shape[0], 1024)]
+            s, q = chunks[0].sum(axis=0), np.square(chunks[0]).sum(axis=0)
+            for c in chunks[1:]:
+                s = s + c.sum(axis=0)
+                q = q + np.square(c).sum(axis=0)
+        self.local_sum += s
+        self.local_sumsq += q
         self.local_count[0] += v.shape[0]
 
     def recompute_stats(self, others=(), world=1):

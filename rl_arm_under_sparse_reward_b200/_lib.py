@@ -83,6 +83,10 @@ SIGNATURES = {
                                     c_void_p]),
     "bmi_ddpg_grad_buffer": (c_int32, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
     "bmi_ddpg_adam_step": (c_int32, [c_void_p, c_void_p]),
+    "bmi_ddpg_p2p_export": (c_int32, [c_void_p, c_void_p]),
+    "bmi_ddpg_p2p_attach": (c_int32, [c_void_p, c_int32, c_int32, c_void_p]),
+    "bmi_ddpg_adam_step_p2p": (c_int32, [c_void_p, c_void_p]),
+    "bmi_ddpg_p2p_status": (c_int32, [c_void_p, POINTER(c_int32)]),
     "bmi_ddpg_soft_update": (c_int32, [c_void_p, c_void_p]),
     "bmi_select_actions": (c_int32, [c_void_p, c_int64, c_int32, c_float, c_float, c_float, c_float,
                                      c_uint64, c_void_p, c_void_p, c_void_p]),

@@ -44,5 +44,6 @@ class Args:
         self.device_rng = True         # Philox draws inside the captured graphs; False -> numpy global stream
         self.late_clip_epoch = 100     # epoch >= 100 clips rollout actions to +-0.15 (ddpg_agent.py:118-119)
         self.use_cuda_graphs = True
+        self.p2p_adam = True           # multi-GPU: fused peer-memory gradient sum + Adam (False: NCCL allreduce, then Adam)
         self.fused_rollout = True      # one kernel launch per batch of episodes (policy MLP inside the env kernel)
         self.verbose = True

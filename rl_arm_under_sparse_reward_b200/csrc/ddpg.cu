@@ -100,6 +100,13 @@ struct bmi_ddpg {
   // policy (act) activations (max_act_rows)
   float *ph1 = nullptr, *ph2 = nullptr, *pz = nullptr;
   std::vector<void*> owned;
+  // ---- peer-memory gradient exchange (fused sum-over-ranks + Adam over NVLink) ----
+  int p2p_rank = 0, p2p_world = 1;
+  int* p2p_sync = nullptr;                 // [0..7] ready flags, [8..15] done flags, [16] epoch, [17] block counter,
+                                           // [18] local go flag, [19] timeout flag   (this rank's copy, IPC-exported)
+  float* peer_grads[8] = {nullptr};        // peer_grads[q] = rank q's gradient buffer mapped here (own buffer for q == rank)
+  int* peer_sync[8] = {nullptr};
+  std::vector<void*> ipc_opened;
 };
 
 namespace bmi {
@@ -320,6 +327,87 @@ __global__ void adam_kernel(float* __restrict__ pa, float* __restrict__ pc, cons
   *p = *p - step * (mi / denom);
 }
 
+// ---- fused gradient sum over ranks + Adam through NVLink peer memory -----------------------------------------
+// Replaces [ncclAllReduce(sum) -> adam_kernel] (utils.py:43-48 + ddpg_agent.py:272,277) by ONE kernel: every rank
+// reads the gradient buffers of all ranks directly (peer loads), adds them in rank order (so every rank computes
+// the identical sum) and applies Adam to its own replica.  Cross-GPU ordering uses two flag barriers in peer
+// memory: "ready" (all backward passes have finished) before the reads, "done" (all ranks have finished reading)
+// before anyone may overwrite its gradients again.  Spins are bounded (about one second) and raise a timeout flag
+// instead of hanging the GPU.
+struct P2PArgs {
+  const float* grads[8];
+  int* sync[8];
+  int rank, world;
+};
+enum { PS_READY = 0, PS_DONE = 8, PS_EPOCH = 16, PS_COUNT = 17, PS_GO = 18, PS_TIMEOUT = 19, PS_WORDS = 32 };
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool spin_until_ge(const int* p, int target, int* timeout_flag) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(p) < target) {
+    if (clock64() - t0 > 2000000000ll) {
+      *timeout_flag = 1;
+      return false;
+    }
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) adam_p2p_kernel(P2PArgs pa, float* __restrict__ p_actor, float* __restrict__ p_critic,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t na,
+                                                       int64_t na_pad, int64_t n, const float* __restrict__ scal, float b1,
+                                                       float b2, float eps) {
+  int* mine = pa.sync[pa.rank];
+  const int epoch = mine[PS_EPOCH] + 1;   // written only by the last block of the previous launch (stream ordered)
+  __shared__ int ok;
+  if (blockIdx.x == 0) {
+    // "ready": tell every rank that this rank's gradients are complete, then wait for everybody
+    if (threadIdx.x < pa.world) {
+      __threadfence_system();
+      st_release_sys(pa.sync[threadIdx.x] + PS_READY + pa.rank, epoch);
+      spin_until_ge(mine + PS_READY + threadIdx.x, epoch, mine + PS_TIMEOUT);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(mine + PS_GO, epoch);
+  } else {
+    if (threadIdx.x == 0) spin_until_ge(mine + PS_GO, epoch, mine + PS_TIMEOUT);
+    __syncthreads();
+  }
+  (void)ok;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= na && i < na_pad) continue;
+    float gi = 0.f;
+    for (int q = 0; q < pa.world; ++q) gi += __ldcv(pa.grads[q] + i);   // rank order: identical sum on every rank
+    float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+    float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / scal[2] + eps;
+    const float step = i < na ? scal[0] : scal[1];
+    float* p = i < na ? p_actor + i : p_critic + (i - na_pad);
+    *p = *p - step * (mi / denom);
+  }
+  // "done": the last block to finish tells every rank that this rank no longer reads their gradients
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int prev = atomicAdd(mine + PS_COUNT, 1);
+    if (prev == (int)gridDim.x - 1) {
+      mine[PS_COUNT] = 0;
+      for (int q = 0; q < pa.world; ++q) st_release_sys(pa.sync[q] + PS_DONE + pa.rank, epoch);
+      for (int q = 0; q < pa.world; ++q) spin_until_ge(mine + PS_DONE + q, epoch, mine + PS_TIMEOUT);
+      st_release_sys(mine + PS_EPOCH, epoch);
+    }
+  }
+}
+
 // target = (1 - polyak) * param + polyak * target, separately rounded like torch
 __global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, int64_t n,
                               float c_src, float c_tgt) {
@@ -494,6 +582,7 @@ extern "C" int bmi_ddpg_destroy(bmi_ddpg* h) {
     cublasLtMatrixLayoutDestroy(kv.second.lb);
     cublasLtMatrixLayoutDestroy(kv.second.lc);
   }
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : h->owned) cudaFree(p);
   if (h->workspace) cudaFree(h->workspace);
   if (h->lt) cublasLtDestroy(h->lt);
@@ -590,6 +679,72 @@ extern "C" int bmi_ddpg_adam_step(bmi_ddpg* h, bmi_stream_t stream) {
                                                             h->la.count, h->na_pad, n, h->adam_scal, c.adam_beta1,
                                                             c.adam_beta2, c.adam_eps);
   BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_p2p_export(bmi_ddpg* h, void* handles128) {
+  BMI_REQUIRE(h && handles128, "bmi_ddpg_p2p_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  if (!h->p2p_sync) {
+    BMI_CUDA_CHECK(cudaMalloc(&h->p2p_sync, PS_WORDS * sizeof(int)));
+    BMI_CUDA_CHECK(cudaMemset(h->p2p_sync, 0, PS_WORDS * sizeof(int)));
+    h->owned.push_back(h->p2p_sync);
+  }
+  cudaIpcMemHandle_t hg, hs;
+  BMI_CUDA_CHECK(cudaIpcGetMemHandle(&hg, h->grads));
+  BMI_CUDA_CHECK(cudaIpcGetMemHandle(&hs, h->p2p_sync));
+  memcpy(handles128, &hg, 64);
+  memcpy((char*)handles128 + 64, &hs, 64);
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_p2p_attach(bmi_ddpg* h, int32_t rank, int32_t world, const void* all_handles) {
+  BMI_REQUIRE(h && all_handles, "bmi_ddpg_p2p_attach: null pointer");
+  BMI_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bmi_ddpg_p2p_attach: bad rank %d / world %d (max 8)", rank, world);
+  BMI_REQUIRE(h->p2p_sync, "bmi_ddpg_p2p_attach: call bmi_ddpg_p2p_export first");
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) {
+      h->peer_grads[q] = h->grads;
+      h->peer_sync[q] = h->p2p_sync;
+      continue;
+    }
+    cudaIpcMemHandle_t hg, hs;
+    memcpy(&hg, (const char*)all_handles + (size_t)q * 128, 64);
+    memcpy(&hs, (const char*)all_handles + (size_t)q * 128 + 64, 64);
+    void *pg = nullptr, *ps = nullptr;
+    BMI_CUDA_CHECK(cudaIpcOpenMemHandle(&pg, hg, cudaIpcMemLazyEnablePeerAccess));
+    BMI_CUDA_CHECK(cudaIpcOpenMemHandle(&ps, hs, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(pg);
+    h->ipc_opened.push_back(ps);
+    h->peer_grads[q] = (float*)pg;
+    h->peer_sync[q] = (int*)ps;
+  }
+  h->p2p_rank = rank;
+  h->p2p_world = world;
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_adam_step_p2p(bmi_ddpg* h, bmi_stream_t stream) {
+  BMI_REQUIRE(h, "bmi_ddpg_adam_step_p2p: null handle");
+  BMI_REQUIRE(h->p2p_world >= 1 && h->peer_grads[h->p2p_rank] != nullptr, "bmi_ddpg_adam_step_p2p: peers not attached");
+  cudaStream_t st = as_stream(stream);
+  const bmi_ddpg_config& c = h->cfg;
+  adam_prepare_kernel<<<1, 1, 0, st>>>(h->adam_step, h->adam_scal, c.lr_actor, c.lr_critic, c.adam_beta1, c.adam_beta2);
+  BMI_LAUNCHED();
+  P2PArgs pa;
+  for (int q = 0; q < 8; ++q) { pa.grads[q] = h->peer_grads[q]; pa.sync[q] = h->peer_sync[q]; }
+  pa.rank = h->p2p_rank;
+  pa.world = h->p2p_world;
+  adam_p2p_kernel<<<64, 256, 0, st>>>(pa, h->actor, h->critic, h->adam_m, h->adam_v, h->la.count, h->na_pad, h->n_grads,
+                                      h->adam_scal, c.adam_beta1, c.adam_beta2, c.adam_eps);
+  BMI_LAUNCHED();
+  return BMI_OK;
+}
+
+extern "C" int bmi_ddpg_p2p_status(bmi_ddpg* h, int32_t* timed_out) {
+  BMI_REQUIRE(h && timed_out, "bmi_ddpg_p2p_status: null pointer");
+  *timed_out = 0;
+  if (h->p2p_sync) BMI_CUDA_CHECK(cudaMemcpy(timed_out, h->p2p_sync + PS_TIMEOUT, sizeof(int), cudaMemcpyDeviceToHost));
   return BMI_OK;
 }
 

@@ -44,6 +44,50 @@ __global__ void norm_update_kernel(const T* __restrict__ vin, int64_t n_rows, in
   if (j == 0) lcount[0] = __fadd_rn(lcount[0], (float)n_rows);  // f32 += python int
 }
 
+// Large inputs (the vectorised agent feeds 2e5 rows per cycle; the reference feeds 100): rows are split into
+// chunks of kNormChunk rows, each chunk is summed sequentially, and the chunk sums are added sequentially in
+// chunk order — a fixed, documented order that oracle/learner_oracle.py restates.  n_rows <= kNormChunk keeps
+// numpy's exact order (one chunk).
+constexpr int kNormChunk = 1024;
+
+template <typename T>
+__global__ void norm_chunk_kernel(const T* __restrict__ vin, int64_t n_rows, int size, double clip,
+                                  double* __restrict__ part) {  // part[chunk][2][size]
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (j >= size) return;
+  const int64_t r0 = c * kNormChunk, r1 = min(n_rows, r0 + (int64_t)kNormChunk);
+  auto ld = [&](int64_t i) { return fmin(fmax((double)vin[i * size + j], -clip), clip); };
+  double s = ld(r0);
+  double q = __dmul_rn(s, s);
+  for (int64_t i = r0 + 1; i < r1; ++i) {
+    const double a = ld(i);
+    s = __dadd_rn(s, a);
+    q = __dadd_rn(q, __dmul_rn(a, a));
+  }
+  part[(c * 2 + 0) * size + j] = s;
+  part[(c * 2 + 1) * size + j] = q;
+}
+
+__global__ void norm_chunk_finish_kernel(const double* __restrict__ part, int64_t n_chunks, int64_t n_rows, int size,
+                                         float* __restrict__ lsum, float* __restrict__ lsumsq,
+                                         float* __restrict__ lcount) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < size) {
+    double s = part[j], q = part[size + j];
+    for (int64_t c = 1; c < n_chunks; ++c) {
+      s = __dadd_rn(s, part[(c * 2 + 0) * size + j]);
+      q = __dadd_rn(q, part[(c * 2 + 1) * size + j]);
+    }
+    lsum[j] = (float)__dadd_rn((double)lsum[j], s);
+    lsumsq[j] = (float)__dadd_rn((double)lsumsq[j], q);
+  }
+  if (j == 0) lcount[0] = __fadd_rn(lcount[0], (float)n_rows);
+}
+
+static double* g_norm_scratch = nullptr;
+static size_t g_norm_scratch_bytes = 0;
+
 __global__ void norm_recompute_kernel(float* lsum, float* lsumsq, float* lcount, float* tsum,
                                       float* tsumsq, float* tcount, float* mean, float* stdv,
                                       int size, float eps, float world) {
@@ -118,6 +162,26 @@ extern "C" int bmi_norm_update(const void* v, int64_t n_rows, int32_t size, int3
   BMI_REQUIRE(dtype == BMI_F32 || dtype == BMI_F64, "bmi_norm_update: bad dtype %d", dtype);
   BMI_REQUIRE(lsum && lsumsq && lcount && (v || n_rows == 0), "bmi_norm_update: null pointer");
   unsigned grid = (unsigned)((size + 31) / 32);
+  if (n_rows > kNormChunk) {  // chunked deterministic order (see norm_chunk_kernel)
+    const int64_t n_chunks = (n_rows + kNormChunk - 1) / kNormChunk;
+    const size_t need = (size_t)n_chunks * 2 * size * sizeof(double);
+    if (need > g_norm_scratch_bytes) {  // grows rarely; not legal inside a stream capture (update() is never captured)
+      if (g_norm_scratch) BMI_CUDA_CHECK(cudaFree(g_norm_scratch));
+      g_norm_scratch = nullptr;
+      g_norm_scratch_bytes = 0;
+      BMI_CUDA_CHECK(cudaMalloc(&g_norm_scratch, need));
+      g_norm_scratch_bytes = need;
+    }
+    dim3 g2(grid, (unsigned)n_chunks);
+    if (dtype == BMI_F64)
+      norm_chunk_kernel<double><<<g2, 32, 0, as_stream(stream)>>>((const double*)v, n_rows, size, clip, g_norm_scratch);
+    else
+      norm_chunk_kernel<float><<<g2, 32, 0, as_stream(stream)>>>((const float*)v, n_rows, size, clip, g_norm_scratch);
+    BMI_LAUNCHED();
+    norm_chunk_finish_kernel<<<grid, 32, 0, as_stream(stream)>>>(g_norm_scratch, n_chunks, n_rows, size, lsum, lsumsq, lcount);
+    BMI_LAUNCHED();
+    return BMI_OK;
+  }
   if (dtype == BMI_F64)
     norm_update_kernel<double><<<grid, 32, 0, as_stream(stream)>>>((const double*)v, n_rows, size, clip,
                                                                    lsum, lsumsq, lcount);

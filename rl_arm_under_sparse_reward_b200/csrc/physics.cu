@@ -262,7 +262,7 @@ __device__ __noinline__ void rnea_lane(const Smem& s, bool is_bias, int unit, fl
   }
 }
 
-// Cholesky of the 9x9 SPD matrix in s.L (lower, in place); lanes cooperate per column.
+// Cholesky of the 9x9 SPD matrix in s.L (lower, in place, reciprocal diagonal); lanes cooperate per column.
 __device__ __noinline__ void chol9(float* Lm, int lane) {
 #pragma unroll 1
   for (int j = 0; j < NL; ++j) {
@@ -270,14 +270,14 @@ __device__ __noinline__ void chol9(float* Lm, int lane) {
     if (lane == 0) {
       d = Lm[j * NL + j];
       for (int k = 0; k < j; ++k) d -= Lm[j * NL + k] * Lm[j * NL + k];
-      d = sqrtf(fmaxf(d, 1e-20f));
+      d = rsqrtf(fmaxf(d, 1e-20f));   // the diagonal stores 1 / L_jj: the solves multiply instead of divide
       Lm[j * NL + j] = d;
     }
     d = __shfl_sync(FULL, d, 0);
     if (lane > j && lane < NL) {
       float sacc = Lm[lane * NL + j];
       for (int k = 0; k < j; ++k) sacc -= Lm[lane * NL + k] * Lm[j * NL + k];
-      Lm[lane * NL + j] = sacc / d;
+      Lm[lane * NL + j] = sacc * d;
     }
     __syncwarp();
   }
@@ -290,14 +290,14 @@ __device__ __forceinline__ void chol9_solve(const float* Lm, const float* b, flo
     float sacc = b[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) sacc -= Lm[i * NL + k] * y[k];
-    y[i] = sacc / Lm[i * NL + i];
+    y[i] = sacc * Lm[i * NL + i];
   }
 #pragma unroll
   for (int i = NL - 1; i >= 0; --i) {
     float sacc = y[i];
 #pragma unroll
     for (int k = i + 1; k < NL; ++k) sacc -= Lm[k * NL + i] * x[k];
-    x[i] = sacc / Lm[i * NL + i];
+    x[i] = sacc * Lm[i * NL + i];
   }
 }
 

@@ -61,6 +61,9 @@ class ddpg_agent:
         gp, gn = ctypes.c_void_p(), ctypes.c_int64()
         _lib.call("bmi_ddpg_grad_buffer", h, ctypes.byref(gp), ctypes.byref(gn))
         self._grad_ptr, self._grad_n = gp, int(gn.value)
+        self._p2p = False
+        if utils.world_size() > 1 and getattr(args, "p2p_adam", True):
+            self._p2p = self._attach_peers()
         # her sampler / replay buffer / demos / normalisers (ddpg_agent.py:44-53)
         self.her_module = her_sampler(args.replay_strategy, args.replay_k, self.vec.compute_reward,
                                       distance_threshold=self.vec.distance_threshold)
@@ -92,6 +95,34 @@ class ddpg_agent:
             os.makedirs(args.save_dir, exist_ok=True)
             self.model_path = os.path.join(args.save_dir, args.env_name)
             os.makedirs(self.model_path, exist_ok=True)
+
+    def _attach_peers(self):
+        """Map every rank's gradient buffer into this process (CUDA IPC over NVLink) for the fused
+        sum-over-ranks + Adam kernel; returns False (NCCL allreduce + Adam is used instead) if the mapping fails."""
+        import torch.distributed as dist
+        buf = (ctypes.c_uint8 * 128)()
+        ok = True
+        try:
+            _lib.call("bmi_ddpg_p2p_export", self._h, ctypes.cast(buf, ctypes.c_void_p))
+        except _lib.BmiError:
+            ok = False
+        gathered = [None] * utils.world_size()
+        dist.all_gather_object(gathered, bytes(buf) if ok else None)
+        if any(g is None for g in gathered):
+            return False
+        allh = (ctypes.c_uint8 * (128 * utils.world_size())).from_buffer_copy(b"".join(gathered))
+        try:
+            _lib.call("bmi_ddpg_p2p_attach", self._h, utils.rank(), utils.world_size(), ctypes.cast(allh, ctypes.c_void_p))
+        except _lib.BmiError:
+            ok = False
+        flags = [None] * utils.world_size()
+        dist.all_gather_object(flags, ok)
+        return all(flags)
+
+    def p2p_timed_out(self):
+        t = ctypes.c_int32(0)
+        _lib.call("bmi_ddpg_p2p_status", self._h, ctypes.byref(t))
+        return bool(t.value)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -252,7 +283,10 @@ class ddpg_agent:
                   _lib.ptr(self._a), _lib.ptr(self._r), st)
         _lib.call("bmi_ddpg_backward", self._h, _lib.ptr(self._x), _lib.ptr(self._xn), _lib.ptr(self._a), _lib.ptr(self._r),
                   _lib.ptr(self._losses), st)
-        if utils.world_size() > 1:   # sync_grads for both nets in ONE collective (SUM, utils.py:43-48)
+        if self._p2p:                # sync_grads of both nets (SUM, utils.py:43-48) fused into the Adam kernel over NVLink
+            _lib.call("bmi_ddpg_adam_step_p2p", self._h, st)
+            return
+        if utils.world_size() > 1:   # NCCL variant: both nets in ONE collective, then Adam
             _lib.call("bmi_comm_allreduce_sum_f32", utils._state["comm"], self._grad_ptr, self._grad_n, st)
         _lib.call("bmi_ddpg_adam_step", self._h, st)
 

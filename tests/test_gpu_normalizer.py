@@ -29,7 +29,7 @@ def test_normalizer_vs_reference_golden(golden_dir):
     assert out.dtype == np.float64 and np.array_equal(out, ref)
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 100, 1037])
+@pytest.mark.parametrize("n", [1, 2, 5, 100, 1024, 1037, 5000])
 def test_update_row_counts_and_preclip(n):
     from rl_arm_under_sparse_reward_b200.normalizer import normalizer
     rng = np.random.RandomState(n)

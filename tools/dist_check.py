@@ -32,8 +32,10 @@ a = Args()
 a.add_demo, a.verbose, a.n_envs, a.buffer_size, a.save_dir = False, False, 64, 1024 * 100, "/tmp/bmi_dc_%d/" % rank
 torch.manual_seed(a.seed + rank)
 env = BmiVecEnv(a.n_envs, seed=a.seed + rank)
+a.p2p_adam = "--nccl" not in sys.argv
 agent = ddpg_agent(a, env, get_env_params(env))
 torch.cuda.synchronize()
+log("p2p adam attached:", agent._p2p)
 log("agent ok; params identical across ranks:", agent.actor_network.flat.sum().item())
 agent.rollout(0)
 agent.buffer.store_episode([agent.ep['obs'], agent.ep['ag'], agent.ep['g'], agent.ep['actions']])
@@ -52,7 +54,10 @@ torch.cuda.synchronize()
 log("graph capture ok")
 agent.update_many(3)
 torch.cuda.synchronize()
-log("graph replay ok; params", agent.actor_network.flat.sum().item(), agent.critic_network.flat.sum().item())
+log("graph replay ok; params", agent.actor_network.flat.sum().item(), agent.critic_network.flat.sum().item(),
+    "p2p timed out:", agent.p2p_timed_out())
+import hashlib
+log("param digest", hashlib.md5(agent.actor_network.flat.cpu().numpy().tobytes() + agent.critic_network.flat.cpu().numpy().tobytes()).hexdigest())
 r = agent._eval_agent()
 log("eval ok", r)
 agent.release_graphs()
