@@ -220,3 +220,27 @@ def test_select_actions_vs_oracle():
     assert int(ctr.item()) == 77 + n
     rand_frac = (np.abs(got - np.clip(pi.cpu().numpy(), -0.15, 0.15)).max(axis=1) > 0.03).mean()
     assert abs(rand_frac - 0.3) < 0.05
+
+
+def test_fused_p2p_adam_world1_equals_plain_adam():
+    """The peer-memory sum + Adam kernel with a single rank (flags and peer pointers all local) must reproduce the
+    plain Adam kernel bit for bit; the 2-GPU equivalence with the NCCL path is tests/test_gpu_multi.py."""
+    from rl_arm_under_sparse_reward_b200 import _lib
+    L = _seeded(8)
+    T1, T2 = Trainer(L), Trainer(L)
+    buf = (ctypes.c_uint8 * 128)()
+    _lib.call("bmi_ddpg_p2p_export", T2.h, ctypes.cast(buf, ctypes.c_void_p))
+    _lib.call("bmi_ddpg_p2p_attach", T2.h, 0, 1, ctypes.cast(buf, ctypes.c_void_p))
+    for i in range(5):
+        x, xn, a, r = _batch(300 + i)
+        T1.backward(x, xn, a, r)
+        T1.adam()
+        T2.backward(x, xn, a, r)
+        _lib.call("bmi_ddpg_adam_step_p2p", T2.h, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    t = ctypes.c_int32(7)
+    _lib.call("bmi_ddpg_p2p_status", T2.h, ctypes.byref(t))
+    assert t.value == 0
+    assert torch.equal(T1.pa, T2.pa) and torch.equal(T1.pc, T2.pc)
+    T1.close()
+    T2.close()
