@@ -21,4 +21,6 @@ for task in ("push", "pick"):
 np.savez_compressed(os.path.join(OUT, "physics_golden.npz"), **out)
 d = np.load(os.path.join(REF, "bmirobot_1000_push_demo.npz"), allow_pickle=True)
 np.savez_compressed(os.path.join(OUT, "demo_small.npz"), obs=d["obs"][:16], ag=d["ag"][:16], g=d["g"][:16], acs=d["acs"][:16])
-print("wrote physics_golden.npz, demo_small.npz")
+d = np.load(os.path.join(REF, "bmirobot_1000_pick_demo.npz"), allow_pickle=True)
+np.savez_compressed(os.path.join(OUT, "demo_small_pick.npz"), obs=d["obs"][:8], ag=d["ag"][:8], g=d["g"][:8], acs=d["acs"][:8])
+print("wrote physics_golden.npz, demo_small.npz, demo_small_pick.npz")
