@@ -32,9 +32,11 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=True):
-    """Compile every CUDA source for sm_100a and link the C-ABI shared library."""
-    if not force and not needs_build():
+def build(force=False, verbose=True, extra_flags=(), lib_path=None, obj_suffix=""):
+    """Compile every CUDA source for sm_100a and link the C-ABI shared library.
+    extra_flags / lib_path / obj_suffix build an instrumented variant next to the product library (tools/)."""
+    lib_path = lib_path or LIB_PATH
+    if not force and lib_path == LIB_PATH and not needs_build():
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = _nvcc()
@@ -45,14 +47,14 @@ def build(force=False, verbose=True):
     common = [
         "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "-Xcompiler", "-fPIC", "-I" + nccl_inc, "-Xptxas", "-v",
-    ]
+    ] + list(extra_flags)
     objs = []
     procs = []
     for src in SOURCES:
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             raise RuntimeError("missing CUDA source " + path)
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OUT_DIR, src.replace(".cu", obj_suffix + ".o"))
         objs.append(obj)
         cmd = [nvcc] + common + ["-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -63,10 +65,10 @@ def build(force=False, verbose=True):
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on " + src)
-    with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
+    with open(os.path.join(OUT_DIR, "ptxas%s.log" % obj_suffix), "w") as f:
         f.write("\n".join(log))
     link = [
-        nvcc, "-shared", "-o", LIB_PATH] + objs + [
+        nvcc, "-shared", "-o", lib_path] + objs + [
         "-L/usr/local/cuda/lib64", "-lcublasLt", "-L" + nccl_lib, "-l:libnccl.so.2",
         "-Xlinker", "-rpath," + nccl_lib, "-Xlinker", "-rpath," + cublas_lib,
         "-Xlinker", "-rpath,/usr/local/cuda/lib64",
@@ -76,8 +78,8 @@ def build(force=False, verbose=True):
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
     if verbose:
-        print("built", LIB_PATH)
-    return LIB_PATH
+        print("built", lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":

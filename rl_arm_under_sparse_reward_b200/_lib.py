@@ -10,7 +10,8 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_in
                     c_uint64, c_void_p)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_C", "libbmi_b200.so")
+# BMI_B200_LIB points the binding at an instrumented build of the same sources (tools/prof_rollout_phases.py)
+LIB_PATH = os.environ.get("BMI_B200_LIB") or os.path.join(HERE, "_C", "libbmi_b200.so")
 
 BMI_F32, BMI_F64 = 0, 1
 TASK_PUSH, TASK_PICK = 0, 1

@@ -32,9 +32,12 @@ constexpr int STAGED = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;  // floa
 constexpr int HID = 256;         // hidden width of the actor (models.py:15-17)
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef BMI_BLOCKS_PER_SM
-#define BMI_BLOCKS_PER_SM 7
+#define BMI_BLOCKS_PER_SM 4
 #endif
-constexpr int BLOCKS_PER_SM = BMI_BLOCKS_PER_SM;  // x WARPS warps: 28 envs per SM -> 4096 envs resident in one wave
+#ifndef BMI_ENVS_PER_BLOCK
+#define BMI_ENVS_PER_BLOCK 7
+#endif
+constexpr int BLOCKS_PER_SM = BMI_BLOCKS_PER_SM;  // x ENVW envs: 28 envs per SM -> 4096 envs resident in one wave
 
 // topology of the right arm: chain 0..6, two fingers on link 6 (checked against the blob)
 __host__ __device__ constexpr int parent_of(int i) { return i == 0 ? -1 : (i <= 6 ? i - 1 : 6); }
@@ -42,21 +45,36 @@ __host__ __device__ constexpr bool is_ancestor_or_self(int a, int l) {
   return a == l || (a <= 6 && l >= a);  // every chain link j<=6 is an ancestor of all l>=j
 }
 
-constexpr int WARPS = 4;        // env instances (warps) per thread block; they share one staged model copy
+// Env instances per thread block: ENVW env warps (one env each) + ONE solver warp that runs the constraint solver of
+// all the block's envs with one LANE per env (solver_loop).  The envs share one staged model copy.  ENVW <= 8 keeps the
+// solver's per-lane shared-memory accesses (env stride = 16 B x odd) free of bank conflicts.
+constexpr int ENVW = BMI_ENVS_PER_BLOCK;
+constexpr int WARPS = ENVW + 1;
+static_assert(ENVW >= 1 && ENVW <= 8, "one solver lane per env, conflict-free for <= 8 envs per block");
+#ifndef BMI_SMEM_PAD
+#define BMI_SMEM_PAD 0
+#endif
+constexpr int MP12 = 12;         // padded row length of the float4-readable 9-vectors (M^-1 columns, arm Jacobian rows)
 
 struct __align__(16) Smem {      // per-env (per-warp) working set
   const float* model;             // block-shared header params + link records (the TMA destination)
+  int req;                        // request sequence number posted by the env warp (-1: the env is finished)
+  int nc, na, n_nc, n_bt;         // contacts, contacts on arm links, non-contact rows, block-on-table contacts
   float R[NL][9], p[NL][3], z[NL][3], c[NL][3], Rl[NL][9];
-  float L[NL * NL], Minv[NL * NL];
+  union {
+    float L[NL * NL];             // mass matrix / its Cholesky factor (dead once M^-1 is known)
+    float4 MinvR4[NL * MP12 / 4]; // motor-row update vectors, rotated: row r holds M^-1[(r+k) % 9][r] at k = 0..8
+  };
+  float4 MinvP4[NL * MP12 / 4];   // M^-1, column r at floats [r*12, r*12+9): one solver row update = 3 float4 loads
   float q[NL], qd[NL], qt[NL], bias[NL], acc[NL];
   float u[16];
+  float dvout[16];                // solver result: velocity deltas of the 15 generalized velocities
   float tauw[NL + 1][NL];             // per-lane RNEA output rows
   float bp[3], bq[4], bv[3], bw[3], goal[3];
   float Rb[9], Ibinv[9], bvert[8][3];
   // contacts
   float cx[MAXC][3], cn[MAXC][3], cdist[MAXC], cmu[MAXC];
   int clink[MAXC], chasb[MAXC];
-  int nc;
   // rows
   union {
     struct {
@@ -64,19 +82,24 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
         float4 rd[3 * MAXC][4];            // per contact row: Jb[6] Wb[6] | invd rhs diag mu
         struct { float A[NL * NL], b[NL]; } ik;   // IK scratch (the IK runs before the sub-steps)
       };
-      float Ja[3 * MAXA][NL], Wa[3 * MAXA][NL];  // arm parts (only contacts that touch an arm link)
+      float4 Ja4[3 * MAXA * MP12 / 4], Wa4[3 * MAXA * MP12 / 4];  // arm parts (only contacts that touch an arm link)
     };
     struct { float x[32], hA[HID], hB[HID]; } pol;  // policy activations (fused rollout; between env steps)
   };
   float obs[BMI_OBS_DIM + BMI_GOAL_DIM];   // last observation + achieved goal (fused rollout)
   int carm[MAXC];                      // arm slot of a contact or -1
-  int na;
   float lam[3 * MAXC];
   float invd[MAXNC], rhs[MAXNC], lo[MAXNC], hi[MAXNC], lamn[MAXNC];  // non-contact rows
   int ncj[MAXNC];                 // joint index (+1, sign = direction) of each non-contact row
   float mdiag[NL];                // diagonal of M^-1
   float qik[NL];
+#if BMI_SMEM_PAD > 0
+  float pad_[BMI_SMEM_PAD];
+#endif
 };
+// the solver warp reads env `lane`'s rows: an env stride of 16 B x odd keeps 8 lanes on distinct banks for both
+// 32-bit and 128-bit shared loads
+static_assert(sizeof(Smem) % 16 == 0 && (sizeof(Smem) / 16) % 2 == 1, "adjust BMI_SMEM_PAD: Smem stride must be 16 B x odd");
 
 struct EnvParams {
   int task;
@@ -85,6 +108,10 @@ struct EnvParams {
 
 __device__ __forceinline__ float P(const Smem& s, int i) { return s.model[i]; }
 __device__ __forceinline__ const float* LK(const Smem& s, int i) { return s.model + BMI_MODEL_HDR + i * BMI_LINK_STRIDE; }
+
+__device__ __forceinline__ float& MINV(Smem& s, int i, int j) { return reinterpret_cast<float*>(s.MinvP4)[j * MP12 + i]; }
+__device__ __forceinline__ float* JA(Smem& s, int row) { return reinterpret_cast<float*>(s.Ja4) + row * MP12; }
+__device__ __forceinline__ float* WA(Smem& s, int row) { return reinterpret_cast<float*>(s.Wa4) + row * MP12; }
 
 __device__ __forceinline__ void cross3(float* o, const float* a, const float* b) {
   float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -107,6 +134,23 @@ __device__ __forceinline__ float warp_sum16(float v) {  // sum over lanes 0..15 
   v += __shfl_xor_sync(FULL, v, 2);
   v += __shfl_xor_sync(FULL, v, 1);
   return v;
+}
+
+// sin and cos for |x| up to a few turns (joint angles, half-angles): two-constant Cody-Waite reduction to [-pi/4, pi/4]
+// + the cephes single-precision minimax polynomials (<= 2 ulp).  Compact on purpose: sincosf() drags a 2 KB slow path
+// into every caller and this kernel is instruction-fetch bound.
+__device__ __forceinline__ void sincos_compact(float x, float* sn, float* cs) {
+  const float kf = rintf(x * 0.63661977236758134f);
+  const int k = (int)kf;
+  float r = fmaf(-kf, 1.5707962513e+00f, x);
+  r = fmaf(-kf, 7.5497894159e-08f, r);
+  const float r2 = r * r;
+  const float ps = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+  const float pc = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2,
+                        fmaf(-0.5f, r2, 1.0f));
+  const float a = (k & 1) ? pc : ps, b = (k & 1) ? ps : pc;
+  *sn = (k & 2) ? -a : a;
+  *cs = ((k + 1) & 2) ? -b : b;
 }
 
 // ---- TMA staging of the joint tree ---------------------------------------------------------
@@ -142,7 +186,7 @@ __device__ __noinline__ void fk(Smem& s, const float* q, int lane) {
     const float* lk = LK(s, lane);
     const float ux = lk[ML_AXIS], uy = lk[ML_AXIS + 1], uz = lk[ML_AXIS + 2];
     float sn, cs;
-    sincosf(q[lane], &sn, &cs);
+    sincos_compact(q[lane], &sn, &cs);
     const float C = 1.f - cs;
     float Rq[9] = {cs + ux * ux * C,      ux * uy * C - uz * sn, ux * uz * C + uy * sn,
                    uy * ux * C + uz * sn, cs + uy * uy * C,      uy * uz * C - ux * sn,
@@ -353,26 +397,24 @@ __device__ __noinline__ void solve_ik(Smem& s, const float* target, int lane) {
 // ---- contact generation ---------------------------------------------------------------------------
 // keep the `cap` lanes with the smallest d (< margin); ties resolved towards the lower lane; returns the
 // ballot mask of the selected lanes
-__device__ __forceinline__ unsigned select_deepest(float d, bool valid, float margin, int cap, int lane) {
+__device__ __noinline__ unsigned select_deepest(float d, bool valid, float margin, int cap, int lane) {
+  // order-preserving map float -> uint, then one REDUX.MIN + one ballot per round (compact: this used to be 25 KB of
+  // unrolled shuffle butterflies, and the kernel is instruction-fetch bound)
+  const unsigned b = __float_as_uint(d);
+  unsigned key = (valid && d < margin) ? (b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u)) : 0xffffffffu;
   unsigned picked = 0;
-  bool cand = valid && d < margin;
+#pragma unroll 1
   for (int r = 0; r < cap; ++r) {
-    float v = cand ? d : 3.0e38f;
-    int idx = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(FULL, v, o);
-      int oi = __shfl_xor_sync(FULL, idx, o);
-      if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-    }
-    if (v >= 3.0e38f) break;
+    const unsigned best = __reduce_min_sync(FULL, key);
+    if (best == 0xffffffffu) break;
+    const int idx = __ffs(__ballot_sync(FULL, key == best)) - 1;  // ties: lower lane
     picked |= 1u << idx;
-    if (lane == idx) cand = false;
+    if (lane == idx) key = 0xffffffffu;
   }
   return picked;
 }
 
-__device__ __forceinline__ void push_contacts(Smem& s, unsigned mask, int lane, int link, int hasb, const float* x,
+__device__ __noinline__ void push_contacts(Smem& s, unsigned mask, int lane, int link, int hasb, const float* x,
                                               const float* n, float dist, float mu) {
   if (mask == 0) return;
   const int base = s.nc, abase = s.na;
@@ -421,6 +463,7 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
     const float d = bvx[2] - tz;
     unsigned m = select_deepest(d, lane < 8, P(s, MP_TABLE_MARGIN), 4, lane);
     push_contacts(s, m, lane, -1, 1, bvx, up, d, ep.bmu * P(s, MP_MU_TABLE));
+    if (lane == 0) s.n_bt = s.nc;  // contacts [0, n_bt) touch no arm link; every later one does
   }
   const int ns = (int)P(s, MP_N_SHAPES);
   const float* shapes = model_g + (int)P(s, MP_SHAPES_OFF);
@@ -456,6 +499,7 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
       matT_vec(xl, s.R[l], r);
       float best = -1e30f;
       int bpi = 0;
+#pragma unroll 2
       for (int pi = 0; pi < np; ++pi) {
         const float4 pl = __ldg(reinterpret_cast<const float4*>(planes) + pi);
         const float sd = pl.x * xl[0] + pl.y * xl[1] + pl.z * xl[2] + pl.w;
@@ -506,7 +550,9 @@ __device__ __forceinline__ void plane_space(const float* n, float* p, float* q) 
 }
 
 // ---- one simulation sub-step ------------------------------------------------------------------------
-__device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, int lane) {
+// substep_pre (one warp per env): dynamics terms, contacts and constraint rows; pgs_thread (one LANE per env) solves;
+// substep_post (one warp per env) integrates.
+__device__ __noinline__ void substep_pre(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, int lane) {
   const float dt = P(s, MP_DT), gz = P(s, MP_GRAVITY), kl = P(s, MP_LIN_DAMP), ka = P(s, MP_ANG_DAMP);
   fk(s, s.q, lane);
   {  // mass matrix columns (lanes 0..8) and bias (lane 9)
@@ -539,13 +585,20 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
     chol9_solve(s.L, b, x);
     if (lane < NL) {
 #pragma unroll
-      for (int i = 0; i < NL; ++i) s.Minv[i * NL + lane] = x[i];
+      for (int i = 0; i < NL; ++i) MINV(s, i, lane) = x[i];
     } else {
 #pragma unroll
       for (int i = 0; i < NL; ++i) s.acc[i] = x[i];
     }
   }
   __syncwarp();
+  // rotated copy for the solver's rolled motor loop (its 9 arm deltas rotate through registers, see solver_loop)
+  for (int idx = lane; idx < NL * NL; idx += 32) {
+    const int r = idx / NL, k = idx - r * NL;
+    int i = r + k;
+    if (i >= NL) i -= NL;
+    reinterpret_cast<float*>(s.MinvR4)[r * MP12 + k] = MINV(s, i, r);
+  }
   // predicted (unconstrained) velocities
   if (lane < NL) s.u[lane] = s.qd[lane] + dt * s.acc[lane];
   else if (lane < 12) {
@@ -568,7 +621,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   const float max_imp = P(s, MP_MOTOR_FORCE) * dt;
   int n_nc = NL;
   if (lane < NL) {
-    const float w = s.Minv[lane * NL + lane];
+    const float w = MINV(s, lane, lane);
     const float target = P(s, MP_MOTOR_KP) * (s.qt[lane] - s.q[lane]) / dt + (1.f - P(s, MP_MOTOR_KD)) * s.qd[lane];
     s.invd[lane] = 1.f / w;
     s.mdiag[lane] = w;
@@ -589,7 +642,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
     const int slot = NL + __popc(m & ((1u << lane) - 1));
     if (viol && slot < MAXNC) {
       const float sgn = side == 0 ? 1.f : -1.f;
-      const float w = s.Minv[j * NL + j];
+      const float w = MINV(s, j, j);
       s.invd[slot] = 1.f / w;
       s.rhs[slot] = (-pen * P(s, MP_ERP_JOINT) / dt - sgn * s.u[j]) / w;
       s.lo[slot] = 0.f; s.hi[slot] = P(s, MP_JOINT_LIMIT_IMPULSE); s.lamn[slot] = 0.f;
@@ -629,8 +682,8 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
       if (link >= 0) {  // arm part, compact runtime loops through this row's shared-memory slot
         const float sgn = hasb ? -1.f : 1.f;
         const int as = s.carm[ci] * 3 + kind;
-        float* Jr = s.Ja[as];
-        float* Wr = s.Wa[as];
+        float* Jr = JA(s, as);
+        float* Wr = WA(s, as);
         for (int j = 0; j < NL; ++j) Jr[j] = 0.f;
 #pragma unroll 1
         for (int j = link; j >= 0; j = parent_of(j)) {  // joints on the path base -> link
@@ -641,7 +694,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
 #pragma unroll 1
         for (int i = 0; i < NL; ++i) {
           float acc = 0.f;
-          for (int j = 0; j < NL; ++j) acc += s.Minv[i * NL + j] * Jr[j];
+          for (int j = 0; j < NL; ++j) acc += MINV(s, i, j) * Jr[j];
           Wr[i] = acc;
           diag += Jr[i] * acc;
           rel += Jr[i] * s.u[i];
@@ -670,107 +723,292 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
     }
   }
   __syncwarp();
-  // ---- projected Gauss-Seidel ---------------------------------------------------------------------------
-  // The solve is a strictly sequential chain (row r needs row r-1's update): what bounds an env with many active
-  // rows is the latency of one row, and — when few warps are left on an SM — the instruction fetch of the loop
-  // body, so the body is kept compact enough for the L0 instruction cache (no unrolling over rows; measured
-  // faster than register-resident unrolled motor rows and than fully replicated state, profiles/r01_*).
-  // State: lane j < 9 owns the arm's dv[j]; the block's six deltas are REPLICATED in every lane (dvb), so
-  // block-only rows (block on table: the common case) need no cross-lane traffic; rows that touch an arm link
-  // reduce their 9-term dot product with one 16-lane butterfly; motor / limit rows (J = +-e_j) need one shuffle.
-  float dv = 0.f;
+  if (lane == 0) s.n_nc = n_nc;
+  __syncwarp();
+}
+
+// ---- projected Gauss-Seidel, ONE THREAD per env, served by the block's solver warp ------------------------------
+// The solve is a strictly sequential chain (row r needs row r-1's update), so a warp per env leaves 31 lanes idle for
+// ~90 % of the sub-step's instructions.  Here lane l of the solver warp owns env slot l of the block: all 15 velocity
+// deltas live in its registers, row records come from the env's shared-memory slot (lane-strided, conflict-free), no
+// shuffles.  Row order, clamps and the residual exit are the oracle's (pgs_solve in oracle/bmi_physics_oracle.c).
+//
+// The solver warp is a SERVER: every trip of its loop advances each busy lane by ONE Gauss-Seidel iteration, lanes are
+// at different iteration numbers of different requests.  An env that converges after 30 iterations gets its answer
+// then, integrates and prepares its next sub-step on its own warp while a neighbour with arm contacts is still
+// grinding through its 150 — no barrier couples the envs (iteration counts: median 32, 12 % of the sub-steps hit 150).
+// Protocol per env slot: the env warp writes its rows, then `req = seq` (fence + volatile store); the solver lane polls
+// `req`, solves and writes dvout, then the solver warp arrives on the slot's named barrier where the env warp is parked.
+
+// Shared-memory loads the compiler must not hoist out of the iteration loop: the M^-1 columns and motor-row scalars are
+// loop invariant, and hoisting 140 floats into registers spills them to LOCAL memory (seen in the SASS).
+__device__ __forceinline__ float4 lds_v4(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_volatile_i(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_i(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+// Named hardware barrier (ids 1..ENVW, id 0 is __syncthreads): the env warp parks in bar.sync — no issue slots burnt,
+// unlike an mbarrier.try_wait loop, whose time-out is short enough that 24 waiting warps took 43 % of the SM's issued
+// instructions — and the solver WARP arrives on it (bar.arrive counts whole warps) when the slot's lane has answered.
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+// env warp side: post request `seq` (>0) for the rows just written, sleep until the solver lane has answered
+__device__ __forceinline__ void solver_request(Smem& s, int seq, int slot, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    sts_volatile_i(&s.req, seq);
+  }
+  named_bar_sync(slot + 1);
+}
+__device__ __forceinline__ void solver_release(Smem& s, int lane) {  // the env is finished: its solver lane retires
+  __syncwarp();
+  if (lane == 0) sts_volatile_i(&s.req, -1);
+}
+
+#ifdef BMI_PROF
+// Debug build only (tools/prof_rollout_phases.py): per-env cycle counters of the fused rollout.
+__device__ unsigned long long g_prof[8192 * 8];
+#define PROF_T0() long long prof_t0 = clock64()
+#define PROF_ADD(e, k) do { const long long t1_ = clock64(); if (lane == 0 && (e) < 8192) g_prof[(e) * 8 + (k)] += (unsigned long long)(t1_ - prof_t0); prof_t0 = t1_; } while (0)
+#define PROF_CNT(e, k, v) do { if (lane == 0 && (e) < 8192) g_prof[(e) * 8 + (k)] += (unsigned long long)(v); } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(e, k)
+#define PROF_CNT(e, k, v)
+#endif
+
+__device__ __noinline__ void solver_loop(Smem* sw, int lane, unsigned live_mask) {
+  const bool mine = lane < ENVW && ((live_mask >> lane) & 1u);
+  Smem& s = sw[mine ? lane : 0];
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(&s);
+  const unsigned a_minvr = sbase + (unsigned)offsetof(Smem, MinvR4), a_minv = sbase + (unsigned)offsetof(Smem, MinvP4),
+                 a_rhs = sbase + (unsigned)offsetof(Smem, rhs), a_invd = sbase + (unsigned)offsetof(Smem, invd),
+                 a_mdiag = sbase + (unsigned)offsetof(Smem, mdiag), a_lamn = sbase + (unsigned)offsetof(Smem, lamn);
+  // arm deltas dv0..dv8 (named registers: the motor loop ROTATES them so that a rolled loop can index "the current
+  // joint" statically; after 9 rows they are back in place) and the block's six deltas
+  float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f, dv3 = 0.f, dv4 = 0.f, dv5 = 0.f, dv6 = 0.f, dv7 = 0.f, dv8 = 0.f;
   float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const bool arm_lane = lane < NL;
-  const int al = arm_lane ? lane : 0;
+  const float max_imp = P(s, MP_MOTOR_FORCE) * P(s, MP_DT);
   const int max_it = (int)P(s, MP_SOLVER_ITERS);
   const float thresh = P(s, MP_RESIDUAL_THRESH);
-  auto row_dot = [&](const float4& r0, const float4& r1, int as_row) -> float {
+  bool busy = false, finished = !mine;
+  int seen = 0, it = 0, n_nc = 0, nc = 0, n_bt = 0;
+#define BMI_ARM_APPLY(w0, w1, w2, d)                                                                        \
+  do {                                                                                                      \
+    dv0 = fmaf((w0).x, (d), dv0); dv1 = fmaf((w0).y, (d), dv1); dv2 = fmaf((w0).z, (d), dv2);               \
+    dv3 = fmaf((w0).w, (d), dv3); dv4 = fmaf((w1).x, (d), dv4); dv5 = fmaf((w1).y, (d), dv5);               \
+    dv6 = fmaf((w1).z, (d), dv6); dv7 = fmaf((w1).w, (d), dv7); dv8 = fmaf((w2), (d), dv8);                 \
+  } while (0)
+  auto arm_dot = [&](const float4* J4) -> float {
+    const float4 j0 = J4[0], j1 = J4[1];
+    const float j2 = reinterpret_cast<const float*>(J4)[8];
+    const float a = j0.x * dv0 + j0.y * dv1 + j0.z * dv2;
+    const float b = j0.w * dv3 + j1.x * dv4 + j1.y * dv5;
+    const float c = j1.z * dv6 + j1.w * dv7 + j2 * dv8;
+    return (a + b) + c;
+  };
+  auto blk_dot = [&](const float4& r0, const float4& r1) -> float {
     const float d0 = r0.x * dvb[0] + r0.y * dvb[1] + r0.z * dvb[2];
     const float d1 = r0.w * dvb[3] + r1.x * dvb[4] + r1.y * dvb[5];
-    float dot = d0 + d1;
-    if (as_row >= 0) {  // uniform branch
-      const float t = arm_lane ? s.Ja[as_row][al] * dv : 0.f;
-      dot += __shfl_sync(FULL, warp_sum16(t), 0);
-    }
-    return dot;
+    return d0 + d1;
   };
-  auto row_apply = [&](const float4& r1, const float4& r2, int as_row, float d) {
+  auto blk_apply = [&](const float4& r1, const float4& r2, float d) {
     dvb[0] = fmaf(r1.z, d, dvb[0]); dvb[1] = fmaf(r1.w, d, dvb[1]); dvb[2] = fmaf(r2.x, d, dvb[2]);
     dvb[3] = fmaf(r2.y, d, dvb[3]); dvb[4] = fmaf(r2.z, d, dvb[4]); dvb[5] = fmaf(r2.w, d, dvb[5]);
-    if (as_row >= 0 && arm_lane) dv = fmaf(s.Wa[as_row][al], d, dv);
   };
-  for (int it = 0; it < max_it; ++it) {
-    float resid = 0.f;
 #pragma unroll 1
-    for (int r = 0; r < NL; ++r) {  // motors: J = e_r, bounds +-max_imp; lane r owns dv[r]
-      float d = s.rhs[r] - __shfl_sync(FULL, dv, r) * s.invd[r];
-      const float old = s.lamn[r];
-      const float sum = fminf(fmaxf(old + d, -max_imp), max_imp);
-      d = sum - old;
-      s.lamn[r] = sum;
-      dv = fmaf(s.Minv[al * NL + r], arm_lane ? d : 0.f, dv);
-      const float res = d * s.mdiag[r];
-      resid = fmaxf(resid, res * res);
-    }
-#pragma unroll 1
-    for (int r = NL; r < n_nc; ++r) {  // violated joint limits: J = +-e_j
-      const int jj = s.ncj[r];
-      const int j = abs(jj) - 1;
-      const float sgn = jj > 0 ? 1.f : -1.f;
-      float d = s.rhs[r] - sgn * __shfl_sync(FULL, dv, j) * s.invd[r];
-      const float old = s.lamn[r];
-      const float sum = fminf(fmaxf(old + d, s.lo[r]), s.hi[r]);
-      d = sum - old;
-      s.lamn[r] = sum;
-      dv = fmaf(sgn * s.Minv[al * NL + j], arm_lane ? d : 0.f, dv);
-      const float res = d * s.mdiag[j];
-      resid = fmaxf(resid, res * res);
-    }
-#pragma unroll 1
-    for (int c = 0; c < nc; ++c) {  // contact normals
-      const float4 r0 = s.rd[c][0], r1 = s.rd[c][1], r2 = s.rd[c][2], r3 = s.rd[c][3];
-      const int as = s.carm[c];
-      const int asr = as >= 0 ? as * 3 : -1;
-      float d = r3.y - row_dot(r0, r1, asr) * r3.x;
-      const float old = s.lam[c];
-      const float sum = fmaxf(old + d, 0.f);
-      d = sum - old;
-      s.lam[c] = sum;
-      row_apply(r1, r2, asr, d);
-      const float res = d * r3.z;
-      resid = fmaxf(resid, res * res);
-    }
-#pragma unroll 1
-    for (int c = 0; c < nc; ++c) {  // friction cones
-      const int ra = nc + 2 * c, rb = ra + 1;
-      const float4 a0 = s.rd[ra][0], a1 = s.rd[ra][1], a2 = s.rd[ra][2], a3 = s.rd[ra][3];
-      const float4 b0 = s.rd[rb][0], b1 = s.rd[rb][1], b2 = s.rd[rb][2], b3 = s.rd[rb][3];
-      const int as = s.carm[c];
-      const int asa = as >= 0 ? as * 3 + 1 : -1, asb = as >= 0 ? as * 3 + 2 : -1;
-      const float lim = a3.w * s.lam[c];
-      const float ja = row_dot(a0, a1, asa), jb = row_dot(b0, b1, asb);
-      const float oa = s.lam[ra], ob = s.lam[rb];
-      float sa = oa + (a3.y - ja * a3.x), sb = ob + (b3.y - jb * b3.x);
-      const float n2 = sa * sa + sb * sb;
-      if (n2 > lim * lim) {
-        const float sc = n2 > 0.f ? lim * rsqrtf(n2) : 0.f;
-        sa *= sc; sb *= sc;
-      }
-      const float da = sa - oa, db = sb - ob;
-      s.lam[ra] = sa; s.lam[rb] = sb;
-      row_apply(a1, a2, asa, da);
-      row_apply(b1, b2, asb, db);
-      const float r1_ = da * a3.z, r2_ = db * b3.z;
-      resid = fmaxf(resid, fmaxf(r1_ * r1_, r2_ * r2_));
-    }
-    if (resid <= thresh) break;
-  }
-  __syncwarp();
-  // ---- integrate ----------------------------------------------------------------------------------------
-  float dvl = dv;
+  while (true) {
+    if (!busy && !finished) {  // poll this slot's request word
+      const int r = lds_volatile_i(&s.req);
+      if (r != seen) {
+        seen = r;
+        if (r < 0) finished = true;
+        else {
+          __threadfence_block();
+          busy = true; it = 0;
+          n_nc = s.n_nc; nc = s.nc; n_bt = s.n_bt;
+          dv0 = dv1 = dv2 = dv3 = dv4 = dv5 = dv6 = dv7 = dv8 = 0.f;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) if (lane == 9 + k) dvl = dvb[k];
-  const float unew = (lane < 16 ? s.u[lane & 15] : 0.f) + dvl;
+          for (int i = 0; i < 6; ++i) dvb[i] = 0.f;
+        }
+      }
+    }
+    if (__ballot_sync(FULL, busy) == 0u) {
+      if (__all_sync(FULL, finished)) break;
+      __nanosleep(100);
+      continue;
+    }
+    bool answered = false;
+    if (busy) {  // ONE Gauss-Seidel iteration of this lane's request
+      float resid = 0.f;
+      // ---- motors: J = e_r, bounds +-max_imp.  Three rows per trip of a rolled loop, rotating the arm registers by
+      // three so that the row's own delta is always dv0 / dv1 / dv2 (M^-1 columns are stored rotated to match).
+#pragma unroll 1
+      for (int r3 = 0; r3 < NL; r3 += 3) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const unsigned o = (unsigned)(r3 + k) * 4u, oc = (unsigned)(r3 + k) * (MP12 * 4u);
+          const float dvr = k == 0 ? dv0 : (k == 1 ? dv1 : dv2);
+          float d = lds_f(a_rhs + o) - dvr * lds_f(a_invd + o);
+          const float old = lds_f(a_lamn + o);
+          const float sum = fminf(fmaxf(old + d, -max_imp), max_imp);
+          d = sum - old;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_lamn + o), "f"(sum) : "memory");
+          // rotated column: entry j multiplies the register that currently holds joint (r + j) % 9, i.e. register
+          // (k + j) % 9 of this unrolled group
+          const float4 w0 = lds_v4(a_minvr + oc), w1 = lds_v4(a_minvr + oc + 16);
+          const float w2 = lds_f(a_minvr + oc + 32);
+          if (k == 0) { BMI_ARM_APPLY(w0, w1, w2, d); }
+          else if (k == 1) {
+            dv1 = fmaf(w0.x, d, dv1); dv2 = fmaf(w0.y, d, dv2); dv3 = fmaf(w0.z, d, dv3); dv4 = fmaf(w0.w, d, dv4);
+            dv5 = fmaf(w1.x, d, dv5); dv6 = fmaf(w1.y, d, dv6); dv7 = fmaf(w1.z, d, dv7); dv8 = fmaf(w1.w, d, dv8);
+            dv0 = fmaf(w2, d, dv0);
+          } else {
+            dv2 = fmaf(w0.x, d, dv2); dv3 = fmaf(w0.y, d, dv3); dv4 = fmaf(w0.z, d, dv4); dv5 = fmaf(w0.w, d, dv5);
+            dv6 = fmaf(w1.x, d, dv6); dv7 = fmaf(w1.y, d, dv7); dv8 = fmaf(w1.z, d, dv8); dv0 = fmaf(w1.w, d, dv0);
+            dv1 = fmaf(w2, d, dv1);
+          }
+          const float res = d * lds_f(a_mdiag + o);
+          resid = fmaxf(resid, res * res);
+        }
+        // rotate by three: register j now holds what register (j + 3) % 9 held
+        const float t0 = dv0, t1 = dv1, t2 = dv2;
+        dv0 = dv3; dv1 = dv4; dv2 = dv5; dv3 = dv6; dv4 = dv7; dv5 = dv8; dv6 = t0; dv7 = t1; dv8 = t2;
+      }
+      // ---- violated joint limits: J = +-e_j (rare; the registers are back in joint order here)
+#pragma unroll 1
+      for (int r = NL; r < n_nc; ++r) {
+        const int jj = s.ncj[r];
+        const int j = abs(jj) - 1;
+        const float sgn = jj > 0 ? 1.f : -1.f;
+        float dvj = dv0;
+        dvj = j == 1 ? dv1 : dvj; dvj = j == 2 ? dv2 : dvj; dvj = j == 3 ? dv3 : dvj; dvj = j == 4 ? dv4 : dvj;
+        dvj = j == 5 ? dv5 : dvj; dvj = j == 6 ? dv6 : dvj; dvj = j == 7 ? dv7 : dvj; dvj = j == 8 ? dv8 : dvj;
+        float d = s.rhs[r] - sgn * dvj * s.invd[r];
+        const float old = s.lamn[r];
+        const float sum = fminf(fmaxf(old + d, s.lo[r]), s.hi[r]);
+        d = sum - old;
+        s.lamn[r] = sum;
+        const unsigned a = a_minv + (unsigned)j * (MP12 * 4u);
+        const float4 w0 = lds_v4(a), w1 = lds_v4(a + 16);
+        const float w2 = lds_f(a + 32);
+        const float sd = sgn * d;
+        BMI_ARM_APPLY(w0, w1, w2, sd);
+        const float res = d * s.mdiag[j];
+        resid = fmaxf(resid, res * res);
+      }
+      // ---- contact normals.  Contacts [0, n_bt) are block-on-table (no arm part, all lanes alike), the rest touch an
+      // arm link: two loops instead of a per-row branch.
+#pragma unroll 1
+      for (int c = 0; c < n_bt; ++c) {
+        const float4 r0 = s.rd[c][0], r1 = s.rd[c][1], r2 = s.rd[c][2], r3 = s.rd[c][3];
+        float d = r3.y - blk_dot(r0, r1) * r3.x;
+        const float old = s.lam[c];
+        const float sum = fmaxf(old + d, 0.f);
+        d = sum - old;
+        s.lam[c] = sum;
+        blk_apply(r1, r2, d);
+        const float res = d * r3.z;
+        resid = fmaxf(resid, res * res);
+      }
+#pragma unroll 1
+      for (int c = n_bt; c < nc; ++c) {
+        const float4 r0 = s.rd[c][0], r1 = s.rd[c][1], r2 = s.rd[c][2], r3 = s.rd[c][3];
+        const int asr = s.carm[c] * 3;
+        float d = r3.y - (blk_dot(r0, r1) + arm_dot(s.Ja4 + asr * (MP12 / 4))) * r3.x;
+        const float old = s.lam[c];
+        const float sum = fmaxf(old + d, 0.f);
+        d = sum - old;
+        s.lam[c] = sum;
+        blk_apply(r1, r2, d);
+        {
+          const float4* W4 = s.Wa4 + asr * (MP12 / 4);
+          const float4 w0 = W4[0], w1 = W4[1];
+          const float w2 = reinterpret_cast<const float*>(W4)[8];
+          BMI_ARM_APPLY(w0, w1, w2, d);
+        }
+        const float res = d * r3.z;
+        resid = fmaxf(resid, res * res);
+      }
+      // ---- friction cones (same split)
+#pragma unroll 1
+      for (int c = 0; c < nc; ++c) {
+        const int ra = nc + 2 * c, rb = ra + 1;
+        const float4 a0 = s.rd[ra][0], a1 = s.rd[ra][1], a2 = s.rd[ra][2], a3 = s.rd[ra][3];
+        const float4 b0 = s.rd[rb][0], b1 = s.rd[rb][1], b2 = s.rd[rb][2], b3 = s.rd[rb][3];
+        const float lim = a3.w * s.lam[c];
+        float ja = blk_dot(a0, a1), jb = blk_dot(b0, b1);
+        const bool arm = c >= n_bt;
+        const int asr = arm ? s.carm[c] * 3 : 0;
+        if (arm) {
+          ja += arm_dot(s.Ja4 + (asr + 1) * (MP12 / 4));
+          jb += arm_dot(s.Ja4 + (asr + 2) * (MP12 / 4));
+        }
+        const float oa = s.lam[ra], ob = s.lam[rb];
+        float sa = oa + (a3.y - ja * a3.x), sb = ob + (b3.y - jb * b3.x);
+        const float n2 = sa * sa + sb * sb;
+        const float sc = n2 > lim * lim ? lim * rsqrtf(n2) : 1.f;  // branch-free cone projection (x * 1 is exact)
+        sa *= sc; sb *= sc;
+        const float da = sa - oa, db = sb - ob;
+        s.lam[ra] = sa; s.lam[rb] = sb;
+        blk_apply(a1, a2, da);
+        blk_apply(b1, b2, db);
+        if (arm) {
+          const float4* Wa = s.Wa4 + (asr + 1) * (MP12 / 4);
+          const float4* Wb = s.Wa4 + (asr + 2) * (MP12 / 4);
+          const float4 u0 = Wa[0], u1 = Wa[1], v0 = Wb[0], v1 = Wb[1];
+          const float u2 = reinterpret_cast<const float*>(Wa)[8], v2 = reinterpret_cast<const float*>(Wb)[8];
+          BMI_ARM_APPLY(u0, u1, u2, da);
+          BMI_ARM_APPLY(v0, v1, v2, db);
+        }
+        const float r1_ = da * a3.z, r2_ = db * b3.z;
+        resid = fmaxf(resid, fmaxf(r1_ * r1_, r2_ * r2_));
+      }
+      ++it;
+      if (resid <= thresh || it >= max_it) {  // answer: velocity deltas, then release the env warp
+        s.dvout[0] = dv0; s.dvout[1] = dv1; s.dvout[2] = dv2; s.dvout[3] = dv3; s.dvout[4] = dv4;
+        s.dvout[5] = dv5; s.dvout[6] = dv6; s.dvout[7] = dv7; s.dvout[8] = dv8;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s.dvout[NL + i] = dvb[i];
+        s.dvout[15] = 0.f;
+#ifdef BMI_PROF
+        s.dvout[15] = (float)it;
+#endif
+        __threadfence_block();
+        busy = false;
+        answered = true;
+      }
+    }
+    // wake the env warps whose lanes answered in this trip (warp-uniform loop: bar.arrive is a whole-warp operation)
+    unsigned fin = __ballot_sync(FULL, answered);
+    while (fin) {
+      const int b = __ffs(fin) - 1;
+      fin &= fin - 1u;
+      named_bar_arrive(b + 1);
+    }
+  }
+#undef BMI_ARM_APPLY
+}
+
+// ---- integrate ----------------------------------------------------------------------------------------
+__device__ __noinline__ void substep_post(Smem& s, int lane) {
+  const float dt = P(s, MP_DT);
+  const float unew = lane < 16 ? s.u[lane] + s.dvout[lane] : 0.f;
   if (lane < NL) {
     s.qd[lane] = unew;
     s.q[lane] += dt * unew;
@@ -784,9 +1022,11 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
   if (lane == 0) {  // quaternion exponential map
     const float wn = sqrtf(dot3(s.bw, s.bw)), th = wn * dt;
     float ax[3];
+    float sh, ch;
+    sincos_compact(0.5f * th, &sh, &ch);
     if (wn < 1e-12f) { ax[0] = s.bw[0] * 0.5f * dt; ax[1] = s.bw[1] * 0.5f * dt; ax[2] = s.bw[2] * 0.5f * dt; }
-    else { const float sc = sinf(0.5f * th) / wn; ax[0] = s.bw[0] * sc; ax[1] = s.bw[1] * sc; ax[2] = s.bw[2] * sc; }
-    const float dq[4] = {ax[0], ax[1], ax[2], cosf(0.5f * th)}, q0[4] = {s.bq[0], s.bq[1], s.bq[2], s.bq[3]};
+    else { const float sc = sh / wn; ax[0] = s.bw[0] * sc; ax[1] = s.bw[1] * sc; ax[2] = s.bw[2] * sc; }
+    const float dq[4] = {ax[0], ax[1], ax[2], ch}, q0[4] = {s.bq[0], s.bq[1], s.bq[2], s.bq[3]};
     float r[4];
     r[3] = dq[3] * q0[3] - dq[0] * q0[0] - dq[1] * q0[1] - dq[2] * q0[2];
     r[0] = dq[3] * q0[0] + dq[0] * q0[3] + dq[1] * q0[2] - dq[2] * q0[1];
@@ -799,7 +1039,7 @@ __device__ void substep(Smem& s, const EnvParams& ep, const float* __restrict__ 
 }
 
 // ---- observation -------------------------------------------------------------------------------------------
-__device__ void observe(Smem& s, int lane, float* __restrict__ obs, float* __restrict__ ag) {
+__device__ __noinline__ void observe(Smem& s, int lane, float* __restrict__ obs, float* __restrict__ ag) {
   fk(s, s.q, lane);
   if (lane == 0) {
     float w[3] = {0, 0, 0}, vo[3] = {0, 0, 0};
@@ -873,41 +1113,54 @@ __device__ __forceinline__ float goal_dist(const Smem& s) {
   const float dx = s.bp[0] - s.goal[0], dy = s.bp[1] - s.goal[1], dz = s.bp[2] - s.goal[2];
   return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 }
-__device__ void env_step_core(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, const float* a_in, int lane);
+// ---- block layout ---------------------------------------------------------------------------------------------
+struct BlockSmem {
+  float model_s[STAGED];
+  unsigned long long mbar;
+  int smsp_of[WARPS];   // SM sub-partition (scheduler) each warp of the block sits on
+  int target_smsp;      // sub-partition this block's solver warp should sit on
+  int pad_[3 + (WARPS % 2 ? 1 : 0)];
+  Smem sw[ENVW];
+};
+static_assert(offsetof(BlockSmem, sw) % 16 == 0, "Smem slots must be 16-byte aligned");
+static_assert((sizeof(BlockSmem) + 1024) * BLOCKS_PER_SM <= 228 * 1024, "BLOCKS_PER_SM blocks (+1 KB reserved each) must fit the SM's 228 KB");
+template <int N> struct PrintSize;
+#ifdef BMI_PRINT_SIZES
+PrintSize<sizeof(Smem)> print_smem_size;
+#endif
+extern __shared__ __align__(16) unsigned char bmi_dyn_smem[];
 
-// ---- kernels ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
-env_step_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, float* __restrict__ state,
-                const float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ ag,
-                float* __restrict__ reward, float* __restrict__ success) {
-  __shared__ __align__(16) float model_s[STAGED];
-  __shared__ unsigned long long mbar_s;
-  __shared__ Smem sw[WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * WARPS + warp;
-  stage_model(model_s, &mbar_s, model_g, threadIdx.x);
-  if (e >= n_envs) return;  // whole warp
-  Smem& s = sw[warp];
-  if (lane == 0) s.model = model_s;
-  __syncwarp();
-  load_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
-  float a[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) a[i] = actions[e * 4 + i];
-  env_step_core(s, ep, model_g, a, lane);
-  observe(s, lane, obs + (size_t)e * BMI_OBS_DIM, ag + (size_t)e * BMI_GOAL_DIM);
-  if (lane == 0) {
-    const float dist = goal_dist(s);
-    const float thr = P(s, MP_DIST_THRESHOLD);
-    if (success) success[e] = dist < thr ? 1.f : 0.f;
-    if (reward) reward[e] = dist > thr ? -1.f : -0.f;
+// Block prologue: stage the model, initialise the per-env mbarriers, elect the solver warp.
+// The four blocks that share an SM each run one latency-bound solver warp; those must sit on DIFFERENT sub-partitions
+// (an early version had all four on scheduler 0: 72 % busy there, 8 % on the other three).  The k-th block to arrive on
+// an SM (atomic counter per SM, never reset: only k mod 4 matters) takes sub-partition k mod 4 and elects its first warp
+// whose hardware slot (%warpid mod 4) lives there.  Returns the solver warp's index in the block.
+__device__ __forceinline__ int block_begin(BlockSmem& bs, const float* __restrict__ model_g, int* __restrict__ sm_arrivals,
+                                           int warp, int lane) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ENVW; ++i) {
+      bs.sw[i].req = 0;
+      bs.sw[i].model = bs.model_s;
+    }
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    bs.target_smsp = atomicAdd(sm_arrivals + (smid & 1023u), 1) & 3;
   }
-  store_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
+  if (lane == 0) {
+    unsigned wid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    bs.smsp_of[warp] = (int)(wid & 3u);
+  }
+  stage_model(bs.model_s, &bs.mbar, model_g, threadIdx.x);  // mbarrier-init fence + __syncthreads inside
+  int solver = WARPS - 1;
+#pragma unroll
+  for (int w = WARPS - 1; w >= 0; --w) if (bs.smsp_of[w] == bs.target_smsp) solver = w;
+  return solver;
 }
 
-// clip, (pick: auto-grip), IK, motor set-points, n_substeps sub-steps  (bmirobot_env_push_F.py:92-101)
-__device__ __noinline__ void env_step_core(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
-                                           const float* a_in, int lane) {
+// clip, (pick: auto-grip), IK, motor set-points  (bmirobot_env_push_F.py:92-101) — one warp per env
+__device__ __noinline__ void env_step_begin(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
+                                            const float* a_in, int lane) {
   float a[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) a[i] = fminf(fmaxf(a_in[i], -0.5f), 0.5f);
@@ -928,8 +1181,67 @@ __device__ __noinline__ void env_step_core(Smem& s, const EnvParams& ep, const f
   else if (lane == 7) s.qt[7] = s.q[7] + a[3];  // sent_hand_moving (bmirobot.py:163-191)
   else if (lane == 8) s.qt[8] = s.q[8] - a[3];
   __syncwarp();
+}
+
+// One env step of this warp's env: n_substeps x [set-up | solve on the solver warp | integrate].  `seq` is
+// the warp's running request number.
+__device__ __forceinline__ void env_step_warp(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
+                                              const float* a_in, int lane, int& seq, int slot, int e) {
+  PROF_T0();
+  env_step_begin(s, ep, model_g, a_in, lane);
+  PROF_ADD(e, 1);
   const int nsub = (int)P(s, MP_N_SUBSTEPS);
-  for (int i = 0; i < nsub; ++i) substep(s, ep, model_g, lane);
+  for (int i = 0; i < nsub; ++i) {
+    substep_pre(s, ep, model_g, lane);
+    PROF_ADD(e, 2);
+    solver_request(s, ++seq, slot, lane);
+    PROF_ADD(e, 3);
+#ifdef BMI_PROF
+    PROF_CNT(e, 5, s.dvout[15]);
+    PROF_CNT(e, 6, s.dvout[15] >= 150.f ? 1 : 0);
+    PROF_CNT(e, 7, s.nc);
+    __syncwarp();
+    if (lane == 0) s.dvout[15] = 0.f;
+    __syncwarp();
+#endif
+    substep_post(s, lane);
+    PROF_ADD(e, 4);
+  }
+}
+
+__device__ __forceinline__ unsigned live_env_mask(int n_envs) {
+  const int left = n_envs - (int)blockIdx.x * ENVW;
+  return left >= ENVW ? ((1u << ENVW) - 1u) : ((1u << max(left, 0)) - 1u);
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
+env_step_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, int* __restrict__ sm_arrivals,
+                float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
+                float* __restrict__ ag, float* __restrict__ reward, float* __restrict__ success) {
+  BlockSmem& bs = *reinterpret_cast<BlockSmem*>(bmi_dyn_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int solver_warp = block_begin(bs, model_g, sm_arrivals, warp, lane);
+  if (warp == solver_warp) { solver_loop(bs.sw, lane, live_env_mask(n_envs)); return; }
+  const int slot = warp < solver_warp ? warp : warp - 1;
+  const int e = blockIdx.x * ENVW + slot;
+  if (e >= n_envs) return;  // whole warp; its slot is not in the live mask
+  Smem& s = bs.sw[slot];
+  int seq = 0;
+  load_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = actions[e * 4 + i];
+  env_step_warp(s, ep, model_g, a, lane, seq, slot, e);
+  solver_release(s, lane);
+  observe(s, lane, obs + (size_t)e * BMI_OBS_DIM, ag + (size_t)e * BMI_GOAL_DIM);
+  if (lane == 0) {
+    const float dist = goal_dist(s);
+    const float thr = P(s, MP_DIST_THRESHOLD);
+    if (success) success[e] = dist < thr ? 1.f : 0.f;
+    if (reward) reward[e] = dist > thr ? -1.f : -0.f;
+  }
+  store_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
 }
 
 // ---- fused rollout: policy MLP + exploration noise + episode record + env step, T steps per launch ---------------
@@ -946,7 +1258,7 @@ struct RolloutArgs {
 };
 
 // one hidden layer: out[HID] = relu(Wt[n_in][HID]^T x + b); lane owns outputs 8*lane .. 8*lane+7
-__device__ __forceinline__ void policy_layer(const float* __restrict__ Wt, const float* __restrict__ b, const float* x,
+__device__ __noinline__ void policy_layer(const float* __restrict__ Wt, const float* __restrict__ b, const float* x,
                                              int n_in, float* out, int lane) {
   float acc[8];
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * lane), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * lane + 1);
@@ -965,32 +1277,39 @@ __device__ __forceinline__ void policy_layer(const float* __restrict__ Wt, const
   __syncwarp();
 }
 
-__device__ __forceinline__ float norm_clip(float v, float m, float sd, float clip) {
+__device__ __noinline__ float norm_clip(float v, float m, float sd, float clip) {
   // ddpg_agent._preproc_inputs: float64 (v - mean) / std, clip, then float32 (same as bmi_preproc_inputs)
   const double z = __ddiv_rn(__dsub_rn((double)v, (double)m), (double)sd);
   return (float)fmin(fmax(z, -(double)clip), (double)clip);
 }
 
+__device__ __noinline__ Philox4 philox_explore(unsigned long long seed, unsigned long long ctr) {
+  return philox4x32_10(seed, ctr, kStreamExplore);
+}
+
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
-rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, float* __restrict__ state, RolloutArgs ra) {
-  __shared__ __align__(16) float model_s[STAGED];
-  __shared__ unsigned long long mbar_s;
-  __shared__ Smem sw[WARPS];
+rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, int* __restrict__ sm_arrivals,
+               float* __restrict__ state, RolloutArgs ra) {
+  BlockSmem& bs = *reinterpret_cast<BlockSmem*>(bmi_dyn_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * WARPS + warp;
-  stage_model(model_s, &mbar_s, model_g, threadIdx.x);
-  if (e >= n_envs) return;
-  Smem& s = sw[warp];
-  if (lane == 0) s.model = model_s;
-  __syncwarp();
+  const int solver_warp = block_begin(bs, model_g, sm_arrivals, warp, lane);
+  if (warp == solver_warp) { solver_loop(bs.sw, lane, live_env_mask(n_envs)); return; }
+  const int slot = warp < solver_warp ? warp : warp - 1;
+  const int e = blockIdx.x * ENVW + slot;
+  if (e >= n_envs) return;  // whole warp; its slot is not in the live mask
+  Smem& s = bs.sw[slot];
+  int seq = 0;
   float* st = state + (size_t)e * BMI_ENV_STATE_DIM;
   if (ra.init != nullptr) {  // reset (bmirobot_env_push_F.py:110-165)
     const float* in = ra.init + (size_t)e * 8;
     for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {
       float v = 0.f;
       if (i >= ST_BPOS && i < ST_BPOS + 3) v = in[i - ST_BPOS];
-      else if (i == ST_BQUAT + 2) v = sinf(0.5f * in[3]);
-      else if (i == ST_BQUAT + 3) v = cosf(0.5f * in[3]);
+      else if (i == ST_BQUAT + 2 || i == ST_BQUAT + 3) {
+        float sy, cy;
+        sincos_compact(0.5f * in[3], &sy, &cy);
+        v = i == ST_BQUAT + 2 ? sy : cy;
+      }
       else if (i >= ST_GOAL && i < ST_GOAL + 3) v = in[4 + i - ST_GOAL];
       st[i] = v;
     }
@@ -1009,6 +1328,8 @@ rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, floa
   const float* b4 = Wt4 + HID * Da;
   const unsigned long long ctr0 = ra.explore ? *ra.counter : 0ull;
   for (int t = 0; t < ra.T; ++t) {
+    PROF_T0();
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
     // ---- record obs / ag / g of step t -----------------------------------------------------------------
     if (ra.ep_obs) {
       if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + t) * Do + lane] = s.obs[lane];
@@ -1032,7 +1353,6 @@ rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, floa
       const float4 w = __ldg(reinterpret_cast<const float4*>(Wt4) + k);
       z[0] = fmaf(hk, w.x, z[0]); z[1] = fmaf(hk, w.y, z[1]); z[2] = fmaf(hk, w.z, z[2]); z[3] = fmaf(hk, w.w, z[3]);
     }
-    float a[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float v = z[j];
@@ -1042,9 +1362,9 @@ rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, floa
     }
     if (ra.explore) {  // _select_actions (ddpg_agent.py:174-184): same Philox stream as bmi_select_actions
       const unsigned long long c = ctr0 + (unsigned long long)t * (unsigned long long)n_envs + (unsigned long long)e;
-      const Philox4 pg = philox4x32_10(ra.seed, 3 * c, kStreamExplore);
-      const Philox4 pu = philox4x32_10(ra.seed, 3 * c + 1, kStreamExplore);
-      const Philox4 pb = philox4x32_10(ra.seed, 3 * c + 2, kStreamExplore);
+      const Philox4 pg = philox_explore(ra.seed, 3 * c);
+      const Philox4 pu = philox_explore(ra.seed, 3 * c + 1);
+      const Philox4 pb = philox_explore(ra.seed, 3 * c + 2);
       const bool take_random = u24(pb.v[0]) < ra.random_eps;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1068,10 +1388,12 @@ rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, floa
       ra.ep_act[((size_t)e * ra.T + t) * Da + lane] = v;
     }
     __syncwarp();
-    // ---- env step -------------------------------------------------------------------------------------------
-    env_step_core(s, ep, model_g, a, lane);
+    // ---- env step (the sub-step solves run on the block's solver warp) -------------------------------------------
+    PROF_ADD(e, 0);
+    env_step_warp(s, ep, model_g, a, lane, seq, slot, e);
     observe(s, lane, s.obs, s.obs + Do);
   }
+  solver_release(s, lane);
   if (ra.ep_obs) {
     if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + ra.T) * Do + lane] = s.obs[lane];
     if (lane < Dg) ra.ep_ag[((size_t)e * (ra.T + 1) + ra.T) * Dg + lane] = s.obs[Do + lane];
@@ -1092,15 +1414,16 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(32 * WARPS)
+constexpr int RESET_WARPS = 4;
+__global__ void __launch_bounds__(32 * RESET_WARPS)
 env_reset_kernel(const float* __restrict__ model_g, int n_envs, float* __restrict__ state,
                  const unsigned char* __restrict__ mask, const float* __restrict__ init, float* __restrict__ obs,
                  float* __restrict__ ag, float* __restrict__ g) {
   __shared__ __align__(16) float model_s[STAGED];
   __shared__ unsigned long long mbar_s;
-  __shared__ Smem sw[WARPS];
+  __shared__ Smem sw[RESET_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * WARPS + warp;
+  const int e = blockIdx.x * RESET_WARPS + warp;
   stage_model(model_s, &mbar_s, model_g, threadIdx.x);
   if (e >= n_envs) return;
   Smem& s = sw[warp];
@@ -1112,8 +1435,11 @@ env_reset_kernel(const float* __restrict__ model_g, int n_envs, float* __restric
     for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {
       float v = 0.f;
       if (i >= ST_BPOS && i < ST_BPOS + 3) v = in[i - ST_BPOS];
-      else if (i == ST_BQUAT + 2) v = sinf(0.5f * in[3]);
-      else if (i == ST_BQUAT + 3) v = cosf(0.5f * in[3]);
+      else if (i == ST_BQUAT + 2 || i == ST_BQUAT + 3) {
+        float sy, cy;
+        sincos_compact(0.5f * in[3], &sy, &cy);
+        v = i == ST_BQUAT + 2 ? sy : cy;
+      }
       else if (i >= ST_GOAL && i < ST_GOAL + 3) v = in[4 + i - ST_GOAL];
       st[i] = v;
     }
@@ -1163,6 +1489,7 @@ struct bmi_env {
   float* model_dev = nullptr;
   float* state_dev = nullptr;
   int64_t model_floats = 0;
+  int* sm_arrivals = nullptr;   // per-SM block arrival counters (solver-warp placement), 1024 ints
 };
 
 extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const void* blob, int64_t bytes) {
@@ -1187,8 +1514,13 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
     BMI_REQUIRE((int)sh[MS_NVERTS] <= 24 && ((int)b[MP_POOL_OFF] + (int)sh[MS_PLANE_OFF]) % 4 == 0,
                 "bmi_env_create: shape %d needs <= 24 vertices and 16-byte aligned planes", si);
   }
+  {  // the env kernels keep ENVW env working sets per block in dynamic shared memory (> 48 KB: opt-in)
+    BMI_CUDA_CHECK(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem)));
+    BMI_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem)));
+  }
   bmi_env* h = new bmi_env();
   h->n_envs = n_envs;
+
   h->ep.task = task;
   const int o = task == BMI_TASK_PUSH ? MP_PUSH_HX : MP_PICK_HX;
   for (int a = 0; a < 3; ++a) h->ep.bh[a] = b[o + a];
@@ -1200,13 +1532,15 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   h->ep.binertia[2] = mm * (lx * lx + ly * ly);
   h->model_floats = n;
   if (cudaMalloc(&h->model_dev, n * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&h->state_dev, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)) != cudaSuccess) {
+      cudaMalloc(&h->state_dev, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&h->sm_arrivals, 1024 * sizeof(int)) != cudaSuccess) {
     set_error("bmi_env_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     bmi_env_destroy(h);
     return BMI_ERR_CUDA;
   }
   BMI_CUDA_CHECK(cudaMemcpy(h->model_dev, blob, n * sizeof(float), cudaMemcpyHostToDevice));
   BMI_CUDA_CHECK(cudaMemset(h->state_dev, 0, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)));
+  BMI_CUDA_CHECK(cudaMemset(h->sm_arrivals, 0, 1024 * sizeof(int)));
   *out = h;
   return BMI_OK;
 }
@@ -1215,6 +1549,7 @@ extern "C" int bmi_env_destroy(bmi_env* h) {
   if (!h) return BMI_OK;
   if (h->model_dev) cudaFree(h->model_dev);
   if (h->state_dev) cudaFree(h->state_dev);
+  if (h->sm_arrivals) cudaFree(h->sm_arrivals);
   delete h;
   return BMI_OK;
 }
@@ -1224,7 +1559,7 @@ extern "C" int32_t bmi_env_num_envs(const bmi_env* h) { return h ? h->n_envs : -
 extern "C" int bmi_env_reset(bmi_env* h, const uint8_t* mask, const float* init, float* obs, float* ag, float* g,
                              bmi_stream_t stream) {
   BMI_REQUIRE(h && init && obs && ag && g, "bmi_env_reset: null pointer");
-  env_reset_kernel<<<(h->n_envs + WARPS - 1) / WARPS, 32 * WARPS, 0, as_stream(stream)>>>(h->model_dev, h->n_envs, h->state_dev, mask,
+  env_reset_kernel<<<(h->n_envs + RESET_WARPS - 1) / RESET_WARPS, 32 * RESET_WARPS, 0, as_stream(stream)>>>(h->model_dev, h->n_envs, h->state_dev, mask,
                                                                                            init, obs, ag, g);
   BMI_LAUNCHED();
   return BMI_OK;
@@ -1242,7 +1577,7 @@ extern "C" int bmi_env_sample_init(bmi_env* h, uint64_t seed, uint64_t* counter,
 extern "C" int bmi_env_step(bmi_env* h, const float* actions, float* obs, float* ag, float* reward, float* success,
                             bmi_stream_t stream) {
   BMI_REQUIRE(h && actions && obs && ag, "bmi_env_step: null pointer");
-  env_step_kernel<<<(h->n_envs + WARPS - 1) / WARPS, 32 * WARPS, 0, as_stream(stream)>>>(h->model_dev, h->ep, h->n_envs, h->state_dev,
+  env_step_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), as_stream(stream)>>>(h->model_dev, h->ep, h->n_envs, h->sm_arrivals, h->state_dev,
                                                                                           actions, obs, ag, reward, success);
   BMI_LAUNCHED();
   return BMI_OK;
@@ -1302,7 +1637,7 @@ extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream
   }
   ra.init = a->init; ra.obs = a->obs; ra.ag = a->ag; ra.g = a->g; ra.success = a->success;
   cudaStream_t st = as_stream(stream);
-  rollout_kernel<<<(h->n_envs + WARPS - 1) / WARPS, 32 * WARPS, 0, st>>>(h->model_dev, h->ep, h->n_envs, h->state_dev, ra);
+  rollout_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->ep, h->n_envs, h->sm_arrivals, h->state_dev, ra);
   BMI_LAUNCHED();
   if (a->explore) {
     advance_counter_kernel3<<<1, 1, 0, st>>>(a->counter, (uint64_t)a->T * (uint64_t)h->n_envs);
@@ -1310,3 +1645,15 @@ extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream
   }
   return BMI_OK;
 }
+
+#ifdef BMI_PROF
+extern "C" int bmi_debug_prof(unsigned long long* host_out, int n_words, int reset) {
+  if (host_out) BMI_CUDA_CHECK(cudaMemcpyFromSymbol(host_out, bmi::g_prof, (size_t)n_words * 8));
+  if (reset) {
+    void* p = nullptr;
+    BMI_CUDA_CHECK(cudaGetSymbolAddress(&p, bmi::g_prof));
+    BMI_CUDA_CHECK(cudaMemset(p, 0, sizeof(unsigned long long) * 8192 * 8));
+  }
+  return BMI_OK;
+}
+#endif
