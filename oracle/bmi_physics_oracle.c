@@ -32,7 +32,7 @@
 #define NL 9
 #define NU 15 /* generalized velocities: 9 joints + block linear 3 + block angular 3 */
 #define MAX_ROWS 192
-#define MAX_CONTACTS 10      /* contacts per sub-step (same caps as the kernel: csrc/physics.cu MAXC / MAXA) */
+#define MAX_CONTACTS 9       /* contacts per sub-step (same caps as the kernel: csrc/physics.cu MAXC / MAXA) */
 #define MAX_ARM_CONTACTS 6   /* ... of which at most 6 involve an arm link; later candidates are dropped */
 #define MAX_SHAPE_V 32
 #define MAX_SHAPE_P 64

@@ -25,17 +25,17 @@ namespace bmi {
 constexpr int NL = 9;          // links / joints of the right arm
 constexpr int NU = 15;         // generalized velocities: 9 joints + block linear 3 + angular 3
 constexpr int EE = 8;          // right_hand2
-constexpr int MAXC = 10;       // contacts per sub-step
+constexpr int MAXC = 9;        // contacts per sub-step (one solver lane each)
 constexpr int MAXA = 6;        // ... of which at most 6 involve an arm link
-constexpr int MAXNC = 17;      // non-contact rows: 9 motors + up to 8 limit rows
+constexpr int MAXR = 3 * MAXC; // contact rows: normal + two friction directions per contact
 constexpr int STAGED = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;  // floats staged by TMA
 constexpr int HID = 256;         // hidden width of the actor (models.py:15-17)
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef BMI_BLOCKS_PER_SM
-#define BMI_BLOCKS_PER_SM 4
+#define BMI_BLOCKS_PER_SM 1
 #endif
 #ifndef BMI_ENVS_PER_BLOCK
-#define BMI_ENVS_PER_BLOCK 7
+#define BMI_ENVS_PER_BLOCK 28
 #endif
 constexpr int BLOCKS_PER_SM = BMI_BLOCKS_PER_SM;  // x ENVW envs: 28 envs per SM -> 4096 envs resident in one wave
 
@@ -45,61 +45,52 @@ __host__ __device__ constexpr bool is_ancestor_or_self(int a, int l) {
   return a == l || (a <= 6 && l >= a);  // every chain link j<=6 is an ancestor of all l>=j
 }
 
-// Env instances per thread block: ENVW env warps (one env each) + ONE solver warp that runs the constraint solver of
-// all the block's envs with one LANE per env (solver_loop).  The envs share one staged model copy.  ENVW <= 8 keeps the
-// solver's per-lane shared-memory accesses (env stride = 16 B x odd) free of bank conflicts.
+// Env instances per thread block: ENVW warps, one env each; the envs only share the staged model copy.
 constexpr int ENVW = BMI_ENVS_PER_BLOCK;
-constexpr int WARPS = ENVW + 1;
-static_assert(ENVW >= 1 && ENVW <= 8, "one solver lane per env, conflict-free for <= 8 envs per block");
-#ifndef BMI_SMEM_PAD
-#define BMI_SMEM_PAD 0
-#endif
-constexpr int MP12 = 12;         // padded row length of the float4-readable 9-vectors (M^-1 columns, arm Jacobian rows)
+constexpr int WARPS = ENVW;
+static_assert(ENVW >= 1 && ENVW <= 32, "one warp per env, at most 1024 threads per block");
+
+// Solver lane map (solve_substep): lanes 0..8 own the joints, 9..14 the block's six velocity components,
+// LANE_CT + c owns contact c (its normal and two friction rows).
+constexpr int LANE_BLK = 9, LANE_CT = 16;
+static_assert(LANE_CT + MAXC <= 32 && MAXR <= 32, "one lane per contact, one lane per contact row in the set-up");
+constexpr int MS = 13;            // row stride of M^-1 (odd: lanes i = 0..8 reading entry (i, j) hit distinct banks)
+constexpr int SCOL_BLK = 9;       // coupling-table columns: [0, 9) joints, [9, 15) block velocity, [15, 15 + MAXR) contact rows
+constexpr int SCOL_CT = 15;
+constexpr int SS = SCOL_CT + MAXR + ((SCOL_CT + MAXR) % 2 == 0 ? 1 : 0);  // odd row stride
+constexpr int MAXSC = 3 * MAXA;   // arm-Jacobian scratch rows
 
 struct __align__(16) Smem {      // per-env (per-warp) working set
   const float* model;             // block-shared header params + link records (the TMA destination)
-  int req;                        // request sequence number posted by the env warp (-1: the env is finished)
-  int nc, na, n_nc, n_bt;         // contacts, contacts on arm links, non-contact rows, block-on-table contacts
-  float R[NL][9], p[NL][3], z[NL][3], c[NL][3], Rl[NL][9];
-  union {
-    float L[NL * NL];             // mass matrix / its Cholesky factor (dead once M^-1 is known)
-    float4 MinvR4[NL * MP12 / 4]; // motor-row update vectors, rotated: row r holds M^-1[(r+k) % 9][r] at k = 0..8
-  };
-  float4 MinvP4[NL * MP12 / 4];   // M^-1, column r at floats [r*12, r*12+9): one solver row update = 3 float4 loads
+  int nc, na;                     // contacts, contacts on arm links
+  float R[NL][9], p[NL][3], z[NL][3], c[NL][3];
+  float Minv[NL * MS];            // M^-1 (symmetric), entry (i, j) at [i * MS + j]
   float q[NL], qd[NL], qt[NL], bias[NL], acc[NL];
   float u[16];
-  float dvout[16];                // solver result: velocity deltas of the 15 generalized velocities
-  float tauw[NL + 1][NL];             // per-lane RNEA output rows
   float bp[3], bq[4], bv[3], bw[3], goal[3];
-  float Rb[9], Ibinv[9], bvert[8][3];
+  float Rb[9], Ibinv[9];
   // contacts
   float cx[MAXC][3], cn[MAXC][3], cdist[MAXC], cmu[MAXC];
-  int clink[MAXC], chasb[MAXC];
-  // rows
+  int clink[MAXC], chasb[MAXC], carm[MAXC];   // carm: arm slot of a contact or -1
+  // Coupling table of the constraint solver.  Row x (one per contact row, x = 3 c + k) holds what a unit impulse on
+  // that row does to every solver variable: [0, 9) the joint velocities (M^-1 Ja^T), [9, 15) the block velocity,
+  // [15 + y] the constraint-space velocity of contact row y (the Delassus entry J_y M^-1 J_x^T).  Row MAXR is zero.
+  float S[(MAXR + 1) * SS];
   union {
     struct {
+      float Rl[NL][9];
       union {
-        float4 rd[3 * MAXC][4];            // per contact row: Jb[6] Wb[6] | invd rhs diag mu
-        struct { float A[NL * NL], b[NL]; } ik;   // IK scratch (the IK runs before the sub-steps)
+        struct { float L[NL * NL], tauw[NL + 1][NL]; };   // mass matrix / Cholesky factor, per-lane RNEA rows
+        struct { float A[NL * NL], b[NL]; } ik;           // IK scratch (the IK runs before the sub-steps)
       };
-      float4 Ja4[3 * MAXA * MP12 / 4], Wa4[3 * MAXA * MP12 / 4];  // arm parts (only contacts that touch an arm link)
-    };
-    struct { float x[32], hA[HID], hB[HID]; } pol;  // policy activations (fused rollout; between env steps)
+    } dyn;                                                // live from fk to the end of contact generation
+    struct { float4 sc[MAXR]; float Ja[MAXSC][NL]; } rows;  // row scalars (invd rhs diag mu) + arm Jacobians: set-up only
+    struct { float x[32], h[HID]; } pol;                  // policy activations (fused rollout; between env steps)
   };
   float obs[BMI_OBS_DIM + BMI_GOAL_DIM];   // last observation + achieved goal (fused rollout)
-  int carm[MAXC];                      // arm slot of a contact or -1
-  float lam[3 * MAXC];
-  float invd[MAXNC], rhs[MAXNC], lo[MAXNC], hi[MAXNC], lamn[MAXNC];  // non-contact rows
-  int ncj[MAXNC];                 // joint index (+1, sign = direction) of each non-contact row
-  float mdiag[NL];                // diagonal of M^-1
   float qik[NL];
-#if BMI_SMEM_PAD > 0
-  float pad_[BMI_SMEM_PAD];
-#endif
+  int prof_iters;
 };
-// the solver warp reads env `lane`'s rows: an env stride of 16 B x odd keeps 8 lanes on distinct banks for both
-// 32-bit and 128-bit shared loads
-static_assert(sizeof(Smem) % 16 == 0 && (sizeof(Smem) / 16) % 2 == 1, "adjust BMI_SMEM_PAD: Smem stride must be 16 B x odd");
 
 struct EnvParams {
   int task;
@@ -109,9 +100,8 @@ struct EnvParams {
 __device__ __forceinline__ float P(const Smem& s, int i) { return s.model[i]; }
 __device__ __forceinline__ const float* LK(const Smem& s, int i) { return s.model + BMI_MODEL_HDR + i * BMI_LINK_STRIDE; }
 
-__device__ __forceinline__ float& MINV(Smem& s, int i, int j) { return reinterpret_cast<float*>(s.MinvP4)[j * MP12 + i]; }
-__device__ __forceinline__ float* JA(Smem& s, int row) { return reinterpret_cast<float*>(s.Ja4) + row * MP12; }
-__device__ __forceinline__ float* WA(Smem& s, int row) { return reinterpret_cast<float*>(s.Wa4) + row * MP12; }
+__device__ __forceinline__ float& MINV(Smem& s, int i, int j) { return s.Minv[i * MS + j]; }
+
 
 __device__ __forceinline__ void cross3(float* o, const float* a, const float* b) {
   float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -196,7 +186,7 @@ __device__ __noinline__ void fk(Smem& s, const float* q, int lane) {
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc)
-        s.Rl[lane][3 * r + cc] = Jr[3 * r] * Rq[cc] + Jr[3 * r + 1] * Rq[3 + cc] + Jr[3 * r + 2] * Rq[6 + cc];
+        s.dyn.Rl[lane][3 * r + cc] = Jr[3 * r] * Rq[cc] + Jr[3 * r + 1] * Rq[3 + cc] + Jr[3 * r + 2] * Rq[6 + cc];
   }
   __syncwarp();
 #pragma unroll 1
@@ -205,8 +195,8 @@ __device__ __noinline__ void fk(Smem& s, const float* q, int lane) {
     if (lane < 9) {
       const int r = lane / 3, cc = lane % 3;
       float v;
-      if (pa < 0) v = s.Rl[i][lane];
-      else v = s.R[pa][3 * r] * s.Rl[i][cc] + s.R[pa][3 * r + 1] * s.Rl[i][3 + cc] + s.R[pa][3 * r + 2] * s.Rl[i][6 + cc];
+      if (pa < 0) v = s.dyn.Rl[i][lane];
+      else v = s.R[pa][3 * r] * s.dyn.Rl[i][cc] + s.R[pa][3 * r + 1] * s.dyn.Rl[i][3 + cc] + s.R[pa][3 * r + 2] * s.dyn.Rl[i][6 + cc];
       s.R[i][lane] = v;
     } else if (lane < 12) {
       const int a = lane - 9;
@@ -370,15 +360,15 @@ __device__ __noinline__ void solve_ik(Smem& s, const float* target, int lane) {
     }
     if (lane < NL) {
 #pragma unroll
-      for (int j = 0; j < NL; ++j) s.ik.A[lane * NL + j] = Arow[j];
-      s.ik.b[lane] = Jc[0] * e[0] + Jc[1] * e[1] + Jc[2] * e[2];
+      for (int j = 0; j < NL; ++j) s.dyn.ik.A[lane * NL + j] = Arow[j];
+      s.dyn.ik.b[lane] = Jc[0] * e[0] + Jc[1] * e[1] + Jc[2] * e[2];
     }
     __syncwarp();
-    chol9(s.ik.A, lane);
+    chol9(s.dyn.ik.A, lane);
     float bb[NL], x[NL];
 #pragma unroll
-    for (int j = 0; j < NL; ++j) bb[j] = s.ik.b[j];
-    chol9_solve(s.ik.A, bb, x);  // every lane solves the same system (cheap, avoids a broadcast)
+    for (int j = 0; j < NL; ++j) bb[j] = s.dyn.ik.b[j];
+    chol9_solve(s.dyn.ik.A, bb, x);  // every lane solves the same system (cheap, avoids a broadcast)
     float mx = 0.f;
 #pragma unroll
     for (int j = 0; j < NL; ++j) mx = fmaxf(mx, fabsf(x[j]));
@@ -455,7 +445,6 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
     float l[3] = {(lane & 1 ? 1.f : -1.f) * ep.bh[0], (lane & 2 ? 1.f : -1.f) * ep.bh[1], (lane & 4 ? 1.f : -1.f) * ep.bh[2]};
     mat_vec(bvx, s.Rb, l);
     bvx[0] += s.bp[0]; bvx[1] += s.bp[1]; bvx[2] += s.bp[2];
-    s.bvert[lane][0] = bvx[0]; s.bvert[lane][1] = bvx[1]; s.bvert[lane][2] = bvx[2];
   }
   __syncwarp();
   const float up[3] = {0.f, 0.f, 1.f};
@@ -463,7 +452,6 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
     const float d = bvx[2] - tz;
     unsigned m = select_deepest(d, lane < 8, P(s, MP_TABLE_MARGIN), 4, lane);
     push_contacts(s, m, lane, -1, 1, bvx, up, d, ep.bmu * P(s, MP_MU_TABLE));
-    if (lane == 0) s.n_bt = s.nc;  // contacts [0, n_bt) touch no arm link; every later one does
   }
   const int ns = (int)P(s, MP_N_SHAPES);
   const float* shapes = model_g + (int)P(s, MP_SHAPES_OFF);
@@ -550,19 +538,19 @@ __device__ __forceinline__ void plane_space(const float* n, float* p, float* q) 
 }
 
 // ---- one simulation sub-step ------------------------------------------------------------------------
-// substep_pre (one warp per env): dynamics terms, contacts and constraint rows; pgs_thread (one LANE per env) solves;
-// substep_post (one warp per env) integrates.
-__device__ __noinline__ void substep_pre(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, int lane) {
+// substep_dynamics: M, bias, M^-1, predicted velocities, contacts.  substep_solve: constraint rows, coupling table,
+// projected Gauss-Seidel, integration.  All on the env's own warp.
+__device__ __noinline__ void substep_dynamics(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, int lane) {
   const float dt = P(s, MP_DT), gz = P(s, MP_GRAVITY), kl = P(s, MP_LIN_DAMP), ka = P(s, MP_ANG_DAMP);
   fk(s, s.q, lane);
   {  // mass matrix columns (lanes 0..8) and bias (lane 9)
     if (lane <= NL) {  // one code path for all ten sweeps (no divergence): unit lanes see zero velocity / gravity
       const bool is_bias = lane == NL;
-      float* tau = s.tauw[lane];
+      float* tau = s.dyn.tauw[lane];
       rnea_lane(s, is_bias, lane, is_bias ? gz : 0.f, is_bias ? kl : 0.f, is_bias ? ka : 0.f, tau);
       for (int i = 0; i < NL; ++i) {
         if (is_bias) s.bias[i] = tau[i];
-        else s.L[i * NL + lane] = tau[i];
+        else s.dyn.L[i * NL + lane] = tau[i];
       }
     }
   }
@@ -570,19 +558,19 @@ __device__ __noinline__ void substep_pre(Smem& s, const EnvParams& ep, const flo
   if (lane < NL) {  // symmetrise (lower triangle is what Cholesky reads)
     float v[NL];
 #pragma unroll
-    for (int j = 0; j < NL; ++j) v[j] = 0.5f * (s.L[lane * NL + j] + s.L[j * NL + lane]);
+    for (int j = 0; j < NL; ++j) v[j] = 0.5f * (s.dyn.L[lane * NL + j] + s.dyn.L[j * NL + lane]);
     __syncwarp(0x1ff);
 #pragma unroll
-    for (int j = 0; j < NL; ++j) s.L[lane * NL + j] = v[j];
+    for (int j = 0; j < NL; ++j) s.dyn.L[lane * NL + j] = v[j];
   }
   __syncwarp();
-  chol9(s.L, lane);
+  chol9(s.dyn.L, lane);
   // M^-1 columns (lanes 0..8) and unconstrained acceleration (lane 9)
   if (lane <= NL) {
     float b[NL], x[NL];
 #pragma unroll
     for (int i = 0; i < NL; ++i) b[i] = lane < NL ? (i == lane ? 1.f : 0.f) : (-LK(s, i)[ML_DAMPING] * s.qd[i] - s.bias[i]);
-    chol9_solve(s.L, b, x);
+    chol9_solve(s.dyn.L, b, x);
     if (lane < NL) {
 #pragma unroll
       for (int i = 0; i < NL; ++i) MINV(s, i, lane) = x[i];
@@ -592,13 +580,6 @@ __device__ __noinline__ void substep_pre(Smem& s, const EnvParams& ep, const flo
     }
   }
   __syncwarp();
-  // rotated copy for the solver's rolled motor loop (its 9 arm deltas rotate through registers, see solver_loop)
-  for (int idx = lane; idx < NL * NL; idx += 32) {
-    const int r = idx / NL, k = idx - r * NL;
-    int i = r + k;
-    if (i >= NL) i -= NL;
-    reinterpret_cast<float*>(s.MinvR4)[r * MP12 + k] = MINV(s, i, r);
-  }
   // predicted (unconstrained) velocities
   if (lane < NL) s.u[lane] = s.qd[lane] + dt * s.acc[lane];
   else if (lane < 12) {
@@ -617,167 +598,14 @@ __device__ __noinline__ void substep_pre(Smem& s, const EnvParams& ep, const flo
                     s.Rb[3 * r + 2] * s.Rb[3 * cc + 2] / ep.binertia[2];
   }
   __syncwarp();
-  // ---- non-contact rows: motors (always) then violated joint limits --------------------------------
-  const float max_imp = P(s, MP_MOTOR_FORCE) * dt;
-  int n_nc = NL;
-  if (lane < NL) {
-    const float w = MINV(s, lane, lane);
-    const float target = P(s, MP_MOTOR_KP) * (s.qt[lane] - s.q[lane]) / dt + (1.f - P(s, MP_MOTOR_KD)) * s.qd[lane];
-    s.invd[lane] = 1.f / w;
-    s.mdiag[lane] = w;
-    s.rhs[lane] = (target - s.u[lane]) / w;
-    s.lo[lane] = -max_imp; s.hi[lane] = max_imp; s.lamn[lane] = 0.f;
-    s.ncj[lane] = lane + 1;
-  }
-  {
-    // limit candidates: lane = 2*j + side
-    bool viol = false;
-    float pen = 0.f;
-    const int j = lane >> 1, side = lane & 1;
-    if (lane < 2 * NL) {
-      pen = side == 0 ? s.q[j] - LK(s, j)[ML_LO] : LK(s, j)[ML_HI] - s.q[j];
-      viol = !(pen > 0.f);
-    }
-    unsigned m = __ballot_sync(FULL, viol);
-    const int slot = NL + __popc(m & ((1u << lane) - 1));
-    if (viol && slot < MAXNC) {
-      const float sgn = side == 0 ? 1.f : -1.f;
-      const float w = MINV(s, j, j);
-      s.invd[slot] = 1.f / w;
-      s.rhs[slot] = (-pen * P(s, MP_ERP_JOINT) / dt - sgn * s.u[j]) / w;
-      s.lo[slot] = 0.f; s.hi[slot] = P(s, MP_JOINT_LIMIT_IMPULSE); s.lamn[slot] = 0.f;
-      s.ncj[slot] = side == 0 ? (j + 1) : -(j + 1);
-    }
-    n_nc = min(MAXNC, NL + __popc(m));
-  }
-  __syncwarp();
-  // ---- contact rows: lane = row (3 rows per contact: normal, tangent 1, tangent 2) ------------------
-  // Row storage: the block part of every row (J and M^-1 J^T over the block's 6 velocities) plus its scalars is
-  // one 64-byte record read with broadcast LDS.128; the arm part (9 + 9 floats) exists only for contacts that
-  // touch an arm link.
-  const int nc = s.nc;
-  const int n_rows_c = 3 * nc;
-  for (int base = 0; base < n_rows_c; base += 32) {
-    const int ri = base + lane;
-    if (ri < n_rows_c) {
-      const int ci = ri < nc ? ri : (ri - nc) / 2;
-      const int kind = ri < nc ? 0 : 1 + ((ri - nc) & 1);
-      float n[3] = {s.cn[ci][0], s.cn[ci][1], s.cn[ci][2]}, dir[3], t1[3], t2[3];
-      plane_space(n, t1, t2);
-#pragma unroll
-      for (int a = 0; a < 3; ++a) dir[a] = kind == 0 ? n[a] : (kind == 1 ? t1[a] : t2[a]);
-      const float x[3] = {s.cx[ci][0], s.cx[ci][1], s.cx[ci][2]};
-      const int link = s.clink[ci], hasb = s.chasb[ci];
-      float J[NU];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) J[a] = 0.f;
-      if (hasb) {
-        float r[3] = {x[0] - s.bp[0], x[1] - s.bp[1], x[2] - s.bp[2]}, t[3];
-        cross3(t, r, dir);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { J[9 + a] = dir[a]; J[12 + a] = t[a]; }
-      }
-      float Wv[NU];
-      float diag = 0.f, rel = 0.f;
-      if (link >= 0) {  // arm part, compact runtime loops through this row's shared-memory slot
-        const float sgn = hasb ? -1.f : 1.f;
-        const int as = s.carm[ci] * 3 + kind;
-        float* Jr = JA(s, as);
-        float* Wr = WA(s, as);
-        for (int j = 0; j < NL; ++j) Jr[j] = 0.f;
-#pragma unroll 1
-        for (int j = link; j >= 0; j = parent_of(j)) {  // joints on the path base -> link
-          float r[3] = {x[0] - s.p[j][0], x[1] - s.p[j][1], x[2] - s.p[j][2]}, cr[3];
-          cross3(cr, s.z[j], r);
-          Jr[j] = sgn * dot3(dir, cr);
-        }
-#pragma unroll 1
-        for (int i = 0; i < NL; ++i) {
-          float acc = 0.f;
-          for (int j = 0; j < NL; ++j) acc += MINV(s, i, j) * Jr[j];
-          Wr[i] = acc;
-          diag += Jr[i] * acc;
-          rel += Jr[i] * s.u[i];
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 3; ++a) Wv[9 + a] = J[9 + a] / ep.bmass;
-      mat_vec(Wv + 12, s.Ibinv, J + 12);
-#pragma unroll
-      for (int a = 9; a < NU; ++a) { diag += J[a] * Wv[a]; rel += J[a] * s.u[a]; }
-      const float invd = 1.f / diag;
-      float rhs;
-      if (kind == 0) {
-        const float pen = s.cdist[ci] + P(s, MP_LINEAR_SLOP);
-        float pos_err = 0.f, vel_err = -rel;
-        if (pen > 0.f) vel_err -= pen / dt; else pos_err = -pen * P(s, MP_ERP_CONTACT) / dt;
-        rhs = (pos_err + vel_err) * invd;
-      } else {
-        rhs = -rel * invd;
-      }
-      s.rd[ri][0] = make_float4(J[9], J[10], J[11], J[12]);
-      s.rd[ri][1] = make_float4(J[13], J[14], Wv[9], Wv[10]);
-      s.rd[ri][2] = make_float4(Wv[11], Wv[12], Wv[13], Wv[14]);
-      s.rd[ri][3] = make_float4(invd, rhs, diag, s.cmu[ci]);
-      s.lam[ri] = 0.f;
-    }
-  }
-  __syncwarp();
-  if (lane == 0) s.n_nc = n_nc;
-  __syncwarp();
 }
 
-// ---- projected Gauss-Seidel, ONE THREAD per env, served by the block's solver warp ------------------------------
-// The solve is a strictly sequential chain (row r needs row r-1's update), so a warp per env leaves 31 lanes idle for
-// ~90 % of the sub-step's instructions.  Here lane l of the solver warp owns env slot l of the block: all 15 velocity
-// deltas live in its registers, row records come from the env's shared-memory slot (lane-strided, conflict-free), no
-// shuffles.  Row order, clamps and the residual exit are the oracle's (pgs_solve in oracle/bmi_physics_oracle.c).
-//
-// The solver warp is a SERVER: every trip of its loop advances each busy lane by ONE Gauss-Seidel iteration, lanes are
-// at different iteration numbers of different requests.  An env that converges after 30 iterations gets its answer
-// then, integrates and prepares its next sub-step on its own warp while a neighbour with arm contacts is still
-// grinding through its 150 — no barrier couples the envs (iteration counts: median 32, 12 % of the sub-steps hit 150).
-// Protocol per env slot: the env warp writes its rows, then `req = seq` (fence + volatile store); the solver lane polls
-// `req`, solves and writes dvout, then the solver warp arrives on the slot's named barrier where the env warp is parked.
-
-// Shared-memory loads the compiler must not hoist out of the iteration loop: the M^-1 columns and motor-row scalars are
-// loop invariant, and hoisting 140 floats into registers spills them to LOCAL memory (seen in the SASS).
-__device__ __forceinline__ float4 lds_v4(unsigned addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
+// Shared-memory loads the compiler must not hoist out of the iteration loop (the coupling coefficients are loop
+// invariant; hoisting them into registers spills to LOCAL memory).
 __device__ __forceinline__ float lds_f(unsigned addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
-}
-__device__ __forceinline__ int lds_volatile_i(const int* p) {
-  int v;
-  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_volatile_i(int* p, int v) {
-  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-// Named hardware barrier (ids 1..ENVW, id 0 is __syncthreads): the env warp parks in bar.sync — no issue slots burnt,
-// unlike an mbarrier.try_wait loop, whose time-out is short enough that 24 waiting warps took 43 % of the SM's issued
-// instructions — and the solver WARP arrives on it (bar.arrive counts whole warps) when the slot's lane has answered.
-__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-
-// env warp side: post request `seq` (>0) for the rows just written, sleep until the solver lane has answered
-__device__ __forceinline__ void solver_request(Smem& s, int seq, int slot, int lane) {
-  __syncwarp();
-  if (lane == 0) {
-    __threadfence_block();
-    sts_volatile_i(&s.req, seq);
-  }
-  named_bar_sync(slot + 1);
-}
-__device__ __forceinline__ void solver_release(Smem& s, int lane) {  // the env is finished: its solver lane retires
-  __syncwarp();
-  if (lane == 0) sts_volatile_i(&s.req, -1);
 }
 
 #ifdef BMI_PROF
@@ -792,223 +620,233 @@ __device__ unsigned long long g_prof[8192 * 8];
 #define PROF_CNT(e, k, v)
 #endif
 
-__device__ __noinline__ void solver_loop(Smem* sw, int lane, unsigned live_mask) {
-  const bool mine = lane < ENVW && ((live_mask >> lane) & 1u);
-  Smem& s = sw[mine ? lane : 0];
-  const unsigned sbase = (unsigned)__cvta_generic_to_shared(&s);
-  const unsigned a_minvr = sbase + (unsigned)offsetof(Smem, MinvR4), a_minv = sbase + (unsigned)offsetof(Smem, MinvP4),
-                 a_rhs = sbase + (unsigned)offsetof(Smem, rhs), a_invd = sbase + (unsigned)offsetof(Smem, invd),
-                 a_mdiag = sbase + (unsigned)offsetof(Smem, mdiag), a_lamn = sbase + (unsigned)offsetof(Smem, lamn);
-  // arm deltas dv0..dv8 (named registers: the motor loop ROTATES them so that a rolled loop can index "the current
-  // joint" statically; after 9 rows they are back in place) and the block's six deltas
-  float dv0 = 0.f, dv1 = 0.f, dv2 = 0.f, dv3 = 0.f, dv4 = 0.f, dv5 = 0.f, dv6 = 0.f, dv7 = 0.f, dv8 = 0.f;
-  float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float max_imp = P(s, MP_MOTOR_FORCE) * P(s, MP_DT);
+// ---- constraint rows + projected Gauss-Seidel + integration ------------------------------------------------------
+// Same rows, row order, clamps and residual exit as pgs_solve in oracle/bmi_physics_oracle.c (Bullet's order: motors,
+// violated joint limits, contact normals, friction cones), but iterated in CONSTRAINT space so that the sequential
+// chain per row is   local clamp -> one warp shuffle -> one FMA per lane:
+//   * lane j < 9 owns joint j: its variable is the joint's velocity delta dv_j; its rows are the motor of joint j and
+//     (if violated) the joint's limit;
+//   * lanes 9..14 own the block's six velocity deltas (no rows of their own);
+//   * lane LANE_CT + c owns contact c: its variables are v_k = J_k . dv for its normal and two friction rows.
+// A row update computes its impulse change d from the owner's registers only, broadcasts d with one shuffle, and every
+// lane adds (coupling coefficient) x d to its variables.  The coefficients are M^-1 (joint -> joint), M^-1 Ja^T
+// (joint <-> contact row), the block's response (contact row -> block velocity) and the Delassus entries J_y M^-1 J_x^T
+// (contact row -> contact row), precomputed once per sub-step into s.Minv / s.S.  In exact arithmetic the iterates are
+// those of the velocity-space solver.
+__device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lane) {
+  const float dt = P(s, MP_DT);
+  const int nc = s.nc, nrows = 3 * nc;
+  const bool has_arm = s.na > 0;        // uniform
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;   // solver variables of this lane
+  float lam0 = 0.f, lam1 = 0.f, lam2 = 0.f, dl0 = 0.f, dl1 = 0.f, dl2 = 0.f;
+  float rhs0 = 0.f, rhs1 = 0.f, rhs2 = 0.f, inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, dg0 = 0.f, dg1 = 0.f, dg2 = 0.f;
+  float mu = 0.f, lsgn = 1.f;
+  const float max_imp = P(s, MP_MOTOR_FORCE) * dt, lim_hi = P(s, MP_JOINT_LIMIT_IMPULSE);
+  bool viol = false;
+  // ---- joint lanes: motor row (always) and limit row (when violated); at most one side can be violated ------------
+  if (lane < NL) {
+    const float w = MINV(s, lane, lane);
+    const float target = P(s, MP_MOTOR_KP) * (s.qt[lane] - s.q[lane]) / dt + (1.f - P(s, MP_MOTOR_KD)) * s.qd[lane];
+    inv0 = 1.f / w; dg0 = w;
+    rhs0 = (target - s.u[lane]) / w;
+    const float pen_lo = s.q[lane] - LK(s, lane)[ML_LO], pen_hi = LK(s, lane)[ML_HI] - s.q[lane];
+    const bool vlo = !(pen_lo > 0.f), vhi = !(pen_hi > 0.f);
+    viol = vlo || vhi;
+    if (viol) {
+      const float pen = vlo ? pen_lo : pen_hi;
+      lsgn = vlo ? 1.f : -1.f;
+      rhs1 = (-pen * P(s, MP_ERP_JOINT) / dt - lsgn * s.u[lane]) / w;
+      inv1 = lsgn / w;   // d = rhs1 - (sgn dv_j) / w
+      dg1 = w;
+    }
+  }
+  unsigned limit_mask = __ballot_sync(FULL, viol);
+  // ---- contact rows: lane = row x = 3 c + k (k = 0 normal, 1 / 2 the friction directions) --------------------------
+  float Jb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int my_as = -1;  // arm-Jacobian scratch row of this lane's contact row, or -1
+  if (lane < nrows) {
+    const int ci = lane / 3, kind = lane - 3 * ci;
+    float n[3] = {s.cn[ci][0], s.cn[ci][1], s.cn[ci][2]}, dir[3], t1[3], t2[3];
+    plane_space(n, t1, t2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) dir[a] = kind == 0 ? n[a] : (kind == 1 ? t1[a] : t2[a]);
+    const float x[3] = {s.cx[ci][0], s.cx[ci][1], s.cx[ci][2]};
+    const int link = s.clink[ci], hasb = s.chasb[ci];
+    float* Srow = s.S + lane * SS;
+    float diag = 0.f, rel = 0.f;
+    if (link >= 0) {  // arm part, compact runtime loops through this row's scratch slot
+      const float sgn = hasb ? -1.f : 1.f;
+      my_as = s.carm[ci] * 3 + kind;
+      float* Jr = s.rows.Ja[my_as];
+      for (int j = 0; j < NL; ++j) Jr[j] = 0.f;
+#pragma unroll 1
+      for (int j = link; j >= 0; j = parent_of(j)) {  // joints on the path base -> link
+        float r[3] = {x[0] - s.p[j][0], x[1] - s.p[j][1], x[2] - s.p[j][2]}, cr[3];
+        cross3(cr, s.z[j], r);
+        Jr[j] = sgn * dot3(dir, cr);
+      }
+#pragma unroll 1
+      for (int i = 0; i < NL; ++i) {
+        float acc = 0.f;
+        for (int j = 0; j < NL; ++j) acc += MINV(s, i, j) * Jr[j];
+        Srow[i] = acc;
+        diag += Jr[i] * acc;
+        rel += Jr[i] * s.u[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NL; ++i) Srow[i] = 0.f;
+    }
+    float Wb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (hasb) {
+      float r[3] = {x[0] - s.bp[0], x[1] - s.bp[1], x[2] - s.bp[2]}, t[3];
+      cross3(t, r, dir);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { Jb[a] = dir[a]; Jb[3 + a] = t[a]; Wb[a] = dir[a] / ep.bmass; }
+      mat_vec(Wb + 3, s.Ibinv, Jb + 3);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { diag += Jb[a] * Wb[a]; rel += Jb[a] * s.u[9 + a]; }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) Srow[SCOL_BLK + a] = Wb[a];
+    const float invd = 1.f / diag;
+    float rhs;
+    if (kind == 0) {
+      const float pen = s.cdist[ci] + P(s, MP_LINEAR_SLOP);
+      float pos_err = 0.f, vel_err = -rel;
+      if (pen > 0.f) vel_err -= pen / dt; else pos_err = -pen * P(s, MP_ERP_CONTACT) / dt;
+      rhs = (pos_err + vel_err) * invd;
+    } else {
+      rhs = -rel * invd;
+    }
+    s.rows.sc[lane] = make_float4(invd, rhs, diag, s.cmu[ci]);
+  }
+  if (lane < SS) s.S[MAXR * SS + lane] = 0.f;   // the zero row
+  __syncwarp();
+  // ---- Delassus entries: lane y fills column SCOL_CT + y of every row x:  J_y . (M^-1 J_x^T) ------------------------
+  {
+    const unsigned arm_rows = __ballot_sync(FULL, my_as >= 0);   // bit x: row x has an arm part
+    float Ja[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) Ja[j] = my_as >= 0 ? s.rows.Ja[my_as][j] : 0.f;
+    const bool mine_arm = my_as >= 0;
+#pragma unroll 1
+    for (int x = 0; x < nrows; ++x) {
+      const float* W = s.S + x * SS;
+      float a = Jb[0] * W[SCOL_BLK] + Jb[1] * W[SCOL_BLK + 1] + Jb[2] * W[SCOL_BLK + 2] + Jb[3] * W[SCOL_BLK + 3] +
+                Jb[4] * W[SCOL_BLK + 4] + Jb[5] * W[SCOL_BLK + 5];
+      if ((arm_rows >> x) & 1u) {   // uniform
+        float b = 0.f;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) b = fmaf(Ja[j], W[j], b);
+        a += mine_arm ? b : 0.f;
+      }
+      if (lane < nrows) s.S[x * SS + SCOL_CT + lane] = a;
+    }
+  }
+  __syncwarp();
+  // ---- owner lanes pick up their rows' scalars; per-lane coefficient addresses --------------------------------------
+  const unsigned s_base = (unsigned)__cvta_generic_to_shared(s.S);
+  const unsigned zero_row = s_base + MAXR * SS * 4u;
+  // joint events (source joint j): coefficient k of this lane at ja_k + 4 j
+  // contact events (source row x): coefficient k of this lane at ca_k + x * SS * 4
+  unsigned ja0 = zero_row, ja1 = zero_row, ja2 = zero_row, ca0 = s_base, ca1 = s_base, ca2 = s_base;
+  const int myc = lane - LANE_CT;
+  if (lane < NL) {
+    ja0 = ja1 = ja2 = (unsigned)__cvta_generic_to_shared(s.Minv) + (unsigned)lane * (MS * 4u);
+    ca0 = ca1 = ca2 = s_base + (unsigned)lane * 4u;
+  } else if (lane < LANE_BLK + 6) {
+    ca0 = ca1 = ca2 = s_base + (unsigned)lane * 4u;   // columns 9..14
+  } else if (myc >= 0 && myc < nc) {
+    const float4 a = s.rows.sc[3 * myc], b = s.rows.sc[3 * myc + 1], c = s.rows.sc[3 * myc + 2];
+    inv0 = a.x; rhs0 = a.y; dg0 = a.z; mu = a.w;
+    inv1 = b.x; rhs1 = b.y; dg1 = b.z;
+    inv2 = c.x; rhs2 = c.y; dg2 = c.z;
+    ja0 = s_base + (unsigned)(3 * myc) * (SS * 4u);
+    ja1 = ja0 + SS * 4u; ja2 = ja1 + SS * 4u;
+    ca0 = s_base + (unsigned)(SCOL_CT + 3 * myc) * 4u;
+    ca1 = ca0 + 4u; ca2 = ca0 + 8u;
+  }
   const int max_it = (int)P(s, MP_SOLVER_ITERS);
   const float thresh = P(s, MP_RESIDUAL_THRESH);
-  bool busy = false, finished = !mine;
-  int seen = 0, it = 0, n_nc = 0, nc = 0, n_bt = 0;
-#define BMI_ARM_APPLY(w0, w1, w2, d)                                                                        \
-  do {                                                                                                      \
-    dv0 = fmaf((w0).x, (d), dv0); dv1 = fmaf((w0).y, (d), dv1); dv2 = fmaf((w0).z, (d), dv2);               \
-    dv3 = fmaf((w0).w, (d), dv3); dv4 = fmaf((w1).x, (d), dv4); dv5 = fmaf((w1).y, (d), dv5);               \
-    dv6 = fmaf((w1).z, (d), dv6); dv7 = fmaf((w1).w, (d), dv7); dv8 = fmaf((w2), (d), dv8);                 \
+  int it = 0;
+  // one joint-source update: every lane adds its coefficient x d
+#define BMI_JOINT_EVENT(joff, dj)                                                         \
+  do {                                                                                    \
+    const float c0_ = lds_f(ja0 + (joff));                                                \
+    if (has_arm) {                                                                        \
+      const float c1_ = lds_f(ja1 + (joff)), c2_ = lds_f(ja2 + (joff));                   \
+      v1 = fmaf(c1_, (dj), v1); v2 = fmaf(c2_, (dj), v2);                                 \
+    }                                                                                     \
+    v0 = fmaf(c0_, (dj), v0);                                                             \
   } while (0)
-  auto arm_dot = [&](const float4* J4) -> float {
-    const float4 j0 = J4[0], j1 = J4[1];
-    const float j2 = reinterpret_cast<const float*>(J4)[8];
-    const float a = j0.x * dv0 + j0.y * dv1 + j0.z * dv2;
-    const float b = j0.w * dv3 + j1.x * dv4 + j1.y * dv5;
-    const float c = j1.z * dv6 + j1.w * dv7 + j2 * dv8;
-    return (a + b) + c;
-  };
-  auto blk_dot = [&](const float4& r0, const float4& r1) -> float {
-    const float d0 = r0.x * dvb[0] + r0.y * dvb[1] + r0.z * dvb[2];
-    const float d1 = r0.w * dvb[3] + r1.x * dvb[4] + r1.y * dvb[5];
-    return d0 + d1;
-  };
-  auto blk_apply = [&](const float4& r1, const float4& r2, float d) {
-    dvb[0] = fmaf(r1.z, d, dvb[0]); dvb[1] = fmaf(r1.w, d, dvb[1]); dvb[2] = fmaf(r2.x, d, dvb[2]);
-    dvb[3] = fmaf(r2.y, d, dvb[3]); dvb[4] = fmaf(r2.z, d, dvb[4]); dvb[5] = fmaf(r2.w, d, dvb[5]);
-  };
 #pragma unroll 1
   while (true) {
-    if (!busy && !finished) {  // poll this slot's request word
-      const int r = lds_volatile_i(&s.req);
-      if (r != seen) {
-        seen = r;
-        if (r < 0) finished = true;
-        else {
-          __threadfence_block();
-          busy = true; it = 0;
-          n_nc = s.n_nc; nc = s.nc; n_bt = s.n_bt;
-          dv0 = dv1 = dv2 = dv3 = dv4 = dv5 = dv6 = dv7 = dv8 = 0.f;
+    // ---- motors: J = e_j, bounds +-max_imp ----------------------------------------------------------------------
 #pragma unroll
-          for (int i = 0; i < 6; ++i) dvb[i] = 0.f;
-        }
-      }
+    for (int j = 0; j < NL; ++j) {
+      const float cand = fminf(fmaxf(lam0 + fmaf(-v0, inv0, rhs0), -max_imp), max_imp);
+      const float d = cand - lam0;
+      const float dj = __shfl_sync(FULL, d, j);
+      if (lane == j) { lam0 = cand; dl0 = d; }
+      BMI_JOINT_EVENT(4u * j, dj);
     }
-    if (__ballot_sync(FULL, busy) == 0u) {
-      if (__all_sync(FULL, finished)) break;
-      __nanosleep(100);
-      continue;
+    // ---- violated joint limits: J = +-e_j, bounds [0, hi] ---------------------------------------------------------
+    for (unsigned m = limit_mask; m; m &= m - 1u) {
+      const int j = __ffs(m) - 1;
+      const float cand = fminf(fmaxf(lam1 + fmaf(-v0, inv1, rhs1), 0.f), lim_hi);
+      const float d = cand - lam1;
+      const float dj = __shfl_sync(FULL, d * lsgn, j);
+      if (lane == j) { lam1 = cand; dl1 = d; }
+      BMI_JOINT_EVENT(4u * (unsigned)j, dj);
     }
-    bool answered = false;
-    if (busy) {  // ONE Gauss-Seidel iteration of this lane's request
-      float resid = 0.f;
-      // ---- motors: J = e_r, bounds +-max_imp.  Three rows per trip of a rolled loop, rotating the arm registers by
-      // three so that the row's own delta is always dv0 / dv1 / dv2 (M^-1 columns are stored rotated to match).
-#pragma unroll 1
-      for (int r3 = 0; r3 < NL; r3 += 3) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const unsigned o = (unsigned)(r3 + k) * 4u, oc = (unsigned)(r3 + k) * (MP12 * 4u);
-          const float dvr = k == 0 ? dv0 : (k == 1 ? dv1 : dv2);
-          float d = lds_f(a_rhs + o) - dvr * lds_f(a_invd + o);
-          const float old = lds_f(a_lamn + o);
-          const float sum = fminf(fmaxf(old + d, -max_imp), max_imp);
-          d = sum - old;
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(a_lamn + o), "f"(sum) : "memory");
-          // rotated column: entry j multiplies the register that currently holds joint (r + j) % 9, i.e. register
-          // (k + j) % 9 of this unrolled group
-          const float4 w0 = lds_v4(a_minvr + oc), w1 = lds_v4(a_minvr + oc + 16);
-          const float w2 = lds_f(a_minvr + oc + 32);
-          if (k == 0) { BMI_ARM_APPLY(w0, w1, w2, d); }
-          else if (k == 1) {
-            dv1 = fmaf(w0.x, d, dv1); dv2 = fmaf(w0.y, d, dv2); dv3 = fmaf(w0.z, d, dv3); dv4 = fmaf(w0.w, d, dv4);
-            dv5 = fmaf(w1.x, d, dv5); dv6 = fmaf(w1.y, d, dv6); dv7 = fmaf(w1.z, d, dv7); dv8 = fmaf(w1.w, d, dv8);
-            dv0 = fmaf(w2, d, dv0);
-          } else {
-            dv2 = fmaf(w0.x, d, dv2); dv3 = fmaf(w0.y, d, dv3); dv4 = fmaf(w0.z, d, dv4); dv5 = fmaf(w0.w, d, dv5);
-            dv6 = fmaf(w1.x, d, dv6); dv7 = fmaf(w1.y, d, dv7); dv8 = fmaf(w1.z, d, dv8); dv0 = fmaf(w1.w, d, dv0);
-            dv1 = fmaf(w2, d, dv1);
-          }
-          const float res = d * lds_f(a_mdiag + o);
-          resid = fmaxf(resid, res * res);
-        }
-        // rotate by three: register j now holds what register (j + 3) % 9 held
-        const float t0 = dv0, t1 = dv1, t2 = dv2;
-        dv0 = dv3; dv1 = dv4; dv2 = dv5; dv3 = dv6; dv4 = dv7; dv5 = dv8; dv6 = t0; dv7 = t1; dv8 = t2;
-      }
-      // ---- violated joint limits: J = +-e_j (rare; the registers are back in joint order here)
-#pragma unroll 1
-      for (int r = NL; r < n_nc; ++r) {
-        const int jj = s.ncj[r];
-        const int j = abs(jj) - 1;
-        const float sgn = jj > 0 ? 1.f : -1.f;
-        float dvj = dv0;
-        dvj = j == 1 ? dv1 : dvj; dvj = j == 2 ? dv2 : dvj; dvj = j == 3 ? dv3 : dvj; dvj = j == 4 ? dv4 : dvj;
-        dvj = j == 5 ? dv5 : dvj; dvj = j == 6 ? dv6 : dvj; dvj = j == 7 ? dv7 : dvj; dvj = j == 8 ? dv8 : dvj;
-        float d = s.rhs[r] - sgn * dvj * s.invd[r];
-        const float old = s.lamn[r];
-        const float sum = fminf(fmaxf(old + d, s.lo[r]), s.hi[r]);
-        d = sum - old;
-        s.lamn[r] = sum;
-        const unsigned a = a_minv + (unsigned)j * (MP12 * 4u);
-        const float4 w0 = lds_v4(a), w1 = lds_v4(a + 16);
-        const float w2 = lds_f(a + 32);
-        const float sd = sgn * d;
-        BMI_ARM_APPLY(w0, w1, w2, sd);
-        const float res = d * s.mdiag[j];
-        resid = fmaxf(resid, res * res);
-      }
-      // ---- contact normals.  Contacts [0, n_bt) are block-on-table (no arm part, all lanes alike), the rest touch an
-      // arm link: two loops instead of a per-row branch.
-#pragma unroll 1
-      for (int c = 0; c < n_bt; ++c) {
-        const float4 r0 = s.rd[c][0], r1 = s.rd[c][1], r2 = s.rd[c][2], r3 = s.rd[c][3];
-        float d = r3.y - blk_dot(r0, r1) * r3.x;
-        const float old = s.lam[c];
-        const float sum = fmaxf(old + d, 0.f);
-        d = sum - old;
-        s.lam[c] = sum;
-        blk_apply(r1, r2, d);
-        const float res = d * r3.z;
-        resid = fmaxf(resid, res * res);
-      }
-#pragma unroll 1
-      for (int c = n_bt; c < nc; ++c) {
-        const float4 r0 = s.rd[c][0], r1 = s.rd[c][1], r2 = s.rd[c][2], r3 = s.rd[c][3];
-        const int asr = s.carm[c] * 3;
-        float d = r3.y - (blk_dot(r0, r1) + arm_dot(s.Ja4 + asr * (MP12 / 4))) * r3.x;
-        const float old = s.lam[c];
-        const float sum = fmaxf(old + d, 0.f);
-        d = sum - old;
-        s.lam[c] = sum;
-        blk_apply(r1, r2, d);
-        {
-          const float4* W4 = s.Wa4 + asr * (MP12 / 4);
-          const float4 w0 = W4[0], w1 = W4[1];
-          const float w2 = reinterpret_cast<const float*>(W4)[8];
-          BMI_ARM_APPLY(w0, w1, w2, d);
-        }
-        const float res = d * r3.z;
-        resid = fmaxf(resid, res * res);
-      }
-      // ---- friction cones (same split)
+    // ---- contact normals ------------------------------------------------------------------------------------------
+    {
+      unsigned a0 = ca0, a1 = ca1, a2 = ca2;
 #pragma unroll 1
       for (int c = 0; c < nc; ++c) {
-        const int ra = nc + 2 * c, rb = ra + 1;
-        const float4 a0 = s.rd[ra][0], a1 = s.rd[ra][1], a2 = s.rd[ra][2], a3 = s.rd[ra][3];
-        const float4 b0 = s.rd[rb][0], b1 = s.rd[rb][1], b2 = s.rd[rb][2], b3 = s.rd[rb][3];
-        const float lim = a3.w * s.lam[c];
-        float ja = blk_dot(a0, a1), jb = blk_dot(b0, b1);
-        const bool arm = c >= n_bt;
-        const int asr = arm ? s.carm[c] * 3 : 0;
-        if (arm) {
-          ja += arm_dot(s.Ja4 + (asr + 1) * (MP12 / 4));
-          jb += arm_dot(s.Ja4 + (asr + 2) * (MP12 / 4));
-        }
-        const float oa = s.lam[ra], ob = s.lam[rb];
-        float sa = oa + (a3.y - ja * a3.x), sb = ob + (b3.y - jb * b3.x);
+        const float c0 = lds_f(a0), c1 = lds_f(a1), c2 = lds_f(a2);
+        const float cand = fmaxf(lam0 + fmaf(-v0, inv0, rhs0), 0.f);
+        const float d = cand - lam0;
+        const float dc = __shfl_sync(FULL, d, LANE_CT + c);
+        if (myc == c) { lam0 = cand; dl0 = d; }
+        v0 = fmaf(c0, dc, v0); v1 = fmaf(c1, dc, v1); v2 = fmaf(c2, dc, v2);
+        a0 += 3u * SS * 4u; a1 += 3u * SS * 4u; a2 += 3u * SS * 4u;
+      }
+    }
+    // ---- friction cones -------------------------------------------------------------------------------------------
+    {
+      unsigned a0 = ca0 + SS * 4u, a1 = ca1 + SS * 4u, a2 = ca2 + SS * 4u;
+#pragma unroll 1
+      for (int c = 0; c < nc; ++c) {
+        const float p0 = lds_f(a0), p1 = lds_f(a1), p2 = lds_f(a2);
+        const float q0 = lds_f(a0 + SS * 4u), q1 = lds_f(a1 + SS * 4u), q2 = lds_f(a2 + SS * 4u);
+        const float lim = mu * lam0;
+        float sa = lam1 + fmaf(-v1, inv1, rhs1), sb = lam2 + fmaf(-v2, inv2, rhs2);
         const float n2 = sa * sa + sb * sb;
         const float sc = n2 > lim * lim ? lim * rsqrtf(n2) : 1.f;  // branch-free cone projection (x * 1 is exact)
         sa *= sc; sb *= sc;
-        const float da = sa - oa, db = sb - ob;
-        s.lam[ra] = sa; s.lam[rb] = sb;
-        blk_apply(a1, a2, da);
-        blk_apply(b1, b2, db);
-        if (arm) {
-          const float4* Wa = s.Wa4 + (asr + 1) * (MP12 / 4);
-          const float4* Wb = s.Wa4 + (asr + 2) * (MP12 / 4);
-          const float4 u0 = Wa[0], u1 = Wa[1], v0 = Wb[0], v1 = Wb[1];
-          const float u2 = reinterpret_cast<const float*>(Wa)[8], v2 = reinterpret_cast<const float*>(Wb)[8];
-          BMI_ARM_APPLY(u0, u1, u2, da);
-          BMI_ARM_APPLY(v0, v1, v2, db);
-        }
-        const float r1_ = da * a3.z, r2_ = db * b3.z;
-        resid = fmaxf(resid, fmaxf(r1_ * r1_, r2_ * r2_));
-      }
-      ++it;
-      if (resid <= thresh || it >= max_it) {  // answer: velocity deltas, then release the env warp
-        s.dvout[0] = dv0; s.dvout[1] = dv1; s.dvout[2] = dv2; s.dvout[3] = dv3; s.dvout[4] = dv4;
-        s.dvout[5] = dv5; s.dvout[6] = dv6; s.dvout[7] = dv7; s.dvout[8] = dv8;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) s.dvout[NL + i] = dvb[i];
-        s.dvout[15] = 0.f;
-#ifdef BMI_PROF
-        s.dvout[15] = (float)it;
-#endif
-        __threadfence_block();
-        busy = false;
-        answered = true;
+        const float da = sa - lam1, db = sb - lam2;
+        const float dac = __shfl_sync(FULL, da, LANE_CT + c), dbc = __shfl_sync(FULL, db, LANE_CT + c);
+        if (myc == c) { lam1 = sa; lam2 = sb; dl1 = da; dl2 = db; }
+        v0 = fmaf(p0, dac, v0); v1 = fmaf(p1, dac, v1); v2 = fmaf(p2, dac, v2);
+        v0 = fmaf(q0, dbc, v0); v1 = fmaf(q1, dbc, v1); v2 = fmaf(q2, dbc, v2);
+        a0 += 3u * SS * 4u; a1 += 3u * SS * 4u; a2 += 3u * SS * 4u;
       }
     }
-    // wake the env warps whose lanes answered in this trip (warp-uniform loop: bar.arrive is a whole-warp operation)
-    unsigned fin = __ballot_sync(FULL, answered);
-    while (fin) {
-      const int b = __ffs(fin) - 1;
-      fin &= fin - 1u;
-      named_bar_arrive(b + 1);
-    }
+    // ---- residual: max over all rows of (impulse change x row diagonal)^2 ------------------------------------------
+    const float r0 = dl0 * dg0, r1 = dl1 * dg1, r2 = dl2 * dg2;
+    const float rl = fmaxf(r0 * r0, fmaxf(r1 * r1, r2 * r2));
+    const float resid = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rl)));   // rl >= 0: uint order = float order
+    ++it;
+    if (resid <= thresh || it >= max_it) break;
   }
-#undef BMI_ARM_APPLY
-}
-
-// ---- integrate ----------------------------------------------------------------------------------------
-__device__ __noinline__ void substep_post(Smem& s, int lane) {
-  const float dt = P(s, MP_DT);
-  const float unew = lane < 16 ? s.u[lane] + s.dvout[lane] : 0.f;
+#undef BMI_JOINT_EVENT
+#ifdef BMI_PROF
+  if (lane == 0) s.prof_iters = it;
+#endif
+  // ---- integrate --------------------------------------------------------------------------------------------------
+  const float unew = lane < NU ? s.u[lane] + v0 : 0.f;
   if (lane < NL) {
     s.qd[lane] = unew;
     s.q[lane] += dt * unew;
@@ -1037,6 +875,7 @@ __device__ __noinline__ void substep_post(Smem& s, int lane) {
   }
   __syncwarp();
 }
+
 
 // ---- observation -------------------------------------------------------------------------------------------
 __device__ __noinline__ void observe(Smem& s, int lane, float* __restrict__ obs, float* __restrict__ ag) {
@@ -1117,11 +956,10 @@ __device__ __forceinline__ float goal_dist(const Smem& s) {
 struct BlockSmem {
   float model_s[STAGED];
   unsigned long long mbar;
-  int smsp_of[WARPS];   // SM sub-partition (scheduler) each warp of the block sits on
-  int target_smsp;      // sub-partition this block's solver warp should sit on
-  int pad_[3 + (WARPS % 2 ? 1 : 0)];
+  int pad_[2];
   Smem sw[ENVW];
 };
+static_assert(sizeof(Smem) % 16 == 0, "Smem slots must be 16-byte aligned");
 static_assert(offsetof(BlockSmem, sw) % 16 == 0, "Smem slots must be 16-byte aligned");
 static_assert((sizeof(BlockSmem) + 1024) * BLOCKS_PER_SM <= 228 * 1024, "BLOCKS_PER_SM blocks (+1 KB reserved each) must fit the SM's 228 KB");
 template <int N> struct PrintSize;
@@ -1130,32 +968,10 @@ PrintSize<sizeof(Smem)> print_smem_size;
 #endif
 extern __shared__ __align__(16) unsigned char bmi_dyn_smem[];
 
-// Block prologue: stage the model, initialise the per-env mbarriers, elect the solver warp.
-// The four blocks that share an SM each run one latency-bound solver warp; those must sit on DIFFERENT sub-partitions
-// (an early version had all four on scheduler 0: 72 % busy there, 8 % on the other three).  The k-th block to arrive on
-// an SM (atomic counter per SM, never reset: only k mod 4 matters) takes sub-partition k mod 4 and elects its first warp
-// whose hardware slot (%warpid mod 4) lives there.  Returns the solver warp's index in the block.
-__device__ __forceinline__ int block_begin(BlockSmem& bs, const float* __restrict__ model_g, int* __restrict__ sm_arrivals,
-                                           int warp, int lane) {
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < ENVW; ++i) {
-      bs.sw[i].req = 0;
-      bs.sw[i].model = bs.model_s;
-    }
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    bs.target_smsp = atomicAdd(sm_arrivals + (smid & 1023u), 1) & 3;
-  }
-  if (lane == 0) {
-    unsigned wid;
-    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-    bs.smsp_of[warp] = (int)(wid & 3u);
-  }
+// Block prologue: stage the model (one TMA bulk copy, shared by the block's envs), point every env slot at it.
+__device__ __forceinline__ void block_begin(BlockSmem& bs, const float* __restrict__ model_g) {
+  if (threadIdx.x < ENVW) bs.sw[threadIdx.x].model = bs.model_s;
   stage_model(bs.model_s, &bs.mbar, model_g, threadIdx.x);  // mbarrier-init fence + __syncthreads inside
-  int solver = WARPS - 1;
-#pragma unroll
-  for (int w = WARPS - 1; w >= 0; --w) if (bs.smsp_of[w] == bs.target_smsp) solver = w;
-  return solver;
 }
 
 // clip, (pick: auto-grip), IK, motor set-points  (bmirobot_env_push_F.py:92-101) — one warp per env
@@ -1183,57 +999,42 @@ __device__ __noinline__ void env_step_begin(Smem& s, const EnvParams& ep, const 
   __syncwarp();
 }
 
-// One env step of this warp's env: n_substeps x [set-up | solve on the solver warp | integrate].  `seq` is
-// the warp's running request number.
+// One env step of this warp's env: n_substeps x [dynamics + contacts | rows + solve + integrate].
 __device__ __forceinline__ void env_step_warp(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
-                                              const float* a_in, int lane, int& seq, int slot, int e) {
+                                              const float* a_in, int lane, int e) {
   PROF_T0();
   env_step_begin(s, ep, model_g, a_in, lane);
   PROF_ADD(e, 1);
   const int nsub = (int)P(s, MP_N_SUBSTEPS);
   for (int i = 0; i < nsub; ++i) {
-    substep_pre(s, ep, model_g, lane);
+    substep_dynamics(s, ep, model_g, lane);
     PROF_ADD(e, 2);
-    solver_request(s, ++seq, slot, lane);
+    substep_solve(s, ep, lane);
     PROF_ADD(e, 3);
 #ifdef BMI_PROF
-    PROF_CNT(e, 5, s.dvout[15]);
-    PROF_CNT(e, 6, s.dvout[15] >= 150.f ? 1 : 0);
+    PROF_CNT(e, 5, s.prof_iters);
+    PROF_CNT(e, 6, s.prof_iters >= 150 ? 1 : 0);
     PROF_CNT(e, 7, s.nc);
-    __syncwarp();
-    if (lane == 0) s.dvout[15] = 0.f;
-    __syncwarp();
 #endif
-    substep_post(s, lane);
-    PROF_ADD(e, 4);
   }
-}
-
-__device__ __forceinline__ unsigned live_env_mask(int n_envs) {
-  const int left = n_envs - (int)blockIdx.x * ENVW;
-  return left >= ENVW ? ((1u << ENVW) - 1u) : ((1u << max(left, 0)) - 1u);
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
-env_step_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, int* __restrict__ sm_arrivals,
+env_step_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs,
                 float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
                 float* __restrict__ ag, float* __restrict__ reward, float* __restrict__ success) {
   BlockSmem& bs = *reinterpret_cast<BlockSmem*>(bmi_dyn_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int solver_warp = block_begin(bs, model_g, sm_arrivals, warp, lane);
-  if (warp == solver_warp) { solver_loop(bs.sw, lane, live_env_mask(n_envs)); return; }
-  const int slot = warp < solver_warp ? warp : warp - 1;
-  const int e = blockIdx.x * ENVW + slot;
-  if (e >= n_envs) return;  // whole warp; its slot is not in the live mask
-  Smem& s = bs.sw[slot];
-  int seq = 0;
+  block_begin(bs, model_g);
+  const int e = blockIdx.x * ENVW + warp;
+  if (e >= n_envs) return;  // whole warp
+  Smem& s = bs.sw[warp];
   load_state(s, state + (size_t)e * BMI_ENV_STATE_DIM, lane);
   float a[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) a[i] = actions[e * 4 + i];
-  env_step_warp(s, ep, model_g, a, lane, seq, slot, e);
-  solver_release(s, lane);
+  env_step_warp(s, ep, model_g, a, lane, e);
   observe(s, lane, obs + (size_t)e * BMI_OBS_DIM, ag + (size_t)e * BMI_GOAL_DIM);
   if (lane == 0) {
     const float dist = goal_dist(s);
@@ -1271,6 +1072,7 @@ __device__ __noinline__ void policy_layer(const float* __restrict__ Wt, const fl
     acc[0] = fmaf(xk, w0.x, acc[0]); acc[1] = fmaf(xk, w0.y, acc[1]); acc[2] = fmaf(xk, w0.z, acc[2]); acc[3] = fmaf(xk, w0.w, acc[3]);
     acc[4] = fmaf(xk, w1.x, acc[4]); acc[5] = fmaf(xk, w1.y, acc[5]); acc[6] = fmaf(xk, w1.z, acc[6]); acc[7] = fmaf(xk, w1.w, acc[7]);
   }
+  __syncwarp();   // out may alias x
   float4* o4 = reinterpret_cast<float4*>(out) + 2 * lane;
   o4[0] = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
   o4[1] = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
@@ -1288,17 +1090,14 @@ __device__ __noinline__ Philox4 philox_explore(unsigned long long seed, unsigned
 }
 
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
-rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, int* __restrict__ sm_arrivals,
+rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs,
                float* __restrict__ state, RolloutArgs ra) {
   BlockSmem& bs = *reinterpret_cast<BlockSmem*>(bmi_dyn_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int solver_warp = block_begin(bs, model_g, sm_arrivals, warp, lane);
-  if (warp == solver_warp) { solver_loop(bs.sw, lane, live_env_mask(n_envs)); return; }
-  const int slot = warp < solver_warp ? warp : warp - 1;
-  const int e = blockIdx.x * ENVW + slot;
-  if (e >= n_envs) return;  // whole warp; its slot is not in the live mask
-  Smem& s = bs.sw[slot];
-  int seq = 0;
+  block_begin(bs, model_g);
+  const int e = blockIdx.x * ENVW + warp;
+  if (e >= n_envs) return;  // whole warp
+  Smem& s = bs.sw[warp];
   float* st = state + (size_t)e * BMI_ENV_STATE_DIM;
   if (ra.init != nullptr) {  // reset (bmirobot_env_push_F.py:110-165)
     const float* in = ra.init + (size_t)e * 8;
@@ -1342,14 +1141,14 @@ rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, int*
     if (lane < Do) s.pol.x[lane] = norm_clip(s.obs[lane], ra.o_mean[lane], ra.o_std[lane], ra.clip_range);
     else if (lane < Dx) s.pol.x[lane] = norm_clip(s.goal[lane - Do], ra.g_mean[lane - Do], ra.g_std[lane - Do], ra.clip_range);
     __syncwarp();
-    policy_layer(Wt1, b1, s.pol.x, Dx, s.pol.hA, lane);
-    policy_layer(Wt2, b2, s.pol.hA, HID, s.pol.hB, lane);
-    policy_layer(Wt3, b3, s.pol.hB, HID, s.pol.hA, lane);
+    policy_layer(Wt1, b1, s.pol.x, Dx, s.pol.h, lane);
+    policy_layer(Wt2, b2, s.pol.h, HID, s.pol.h, lane);   // in place: every lane has read all inputs before any stores
+    policy_layer(Wt3, b3, s.pol.h, HID, s.pol.h, lane);
     float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const int k = lane * 8 + kk;
-      const float hk = s.pol.hA[k];
+      const float hk = s.pol.h[k];
       const float4 w = __ldg(reinterpret_cast<const float4*>(Wt4) + k);
       z[0] = fmaf(hk, w.x, z[0]); z[1] = fmaf(hk, w.y, z[1]); z[2] = fmaf(hk, w.z, z[2]); z[3] = fmaf(hk, w.w, z[3]);
     }
@@ -1390,10 +1189,9 @@ rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs, int*
     __syncwarp();
     // ---- env step (the sub-step solves run on the block's solver warp) -------------------------------------------
     PROF_ADD(e, 0);
-    env_step_warp(s, ep, model_g, a, lane, seq, slot, e);
+    env_step_warp(s, ep, model_g, a, lane, e);
     observe(s, lane, s.obs, s.obs + Do);
   }
-  solver_release(s, lane);
   if (ra.ep_obs) {
     if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + ra.T) * Do + lane] = s.obs[lane];
     if (lane < Dg) ra.ep_ag[((size_t)e * (ra.T + 1) + ra.T) * Dg + lane] = s.obs[Do + lane];
@@ -1489,7 +1287,6 @@ struct bmi_env {
   float* model_dev = nullptr;
   float* state_dev = nullptr;
   int64_t model_floats = 0;
-  int* sm_arrivals = nullptr;   // per-SM block arrival counters (solver-warp placement), 1024 ints
 };
 
 extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const void* blob, int64_t bytes) {
@@ -1532,15 +1329,13 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   h->ep.binertia[2] = mm * (lx * lx + ly * ly);
   h->model_floats = n;
   if (cudaMalloc(&h->model_dev, n * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&h->state_dev, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&h->sm_arrivals, 1024 * sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&h->state_dev, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)) != cudaSuccess) {
     set_error("bmi_env_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     bmi_env_destroy(h);
     return BMI_ERR_CUDA;
   }
   BMI_CUDA_CHECK(cudaMemcpy(h->model_dev, blob, n * sizeof(float), cudaMemcpyHostToDevice));
   BMI_CUDA_CHECK(cudaMemset(h->state_dev, 0, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)));
-  BMI_CUDA_CHECK(cudaMemset(h->sm_arrivals, 0, 1024 * sizeof(int)));
   *out = h;
   return BMI_OK;
 }
@@ -1549,7 +1344,6 @@ extern "C" int bmi_env_destroy(bmi_env* h) {
   if (!h) return BMI_OK;
   if (h->model_dev) cudaFree(h->model_dev);
   if (h->state_dev) cudaFree(h->state_dev);
-  if (h->sm_arrivals) cudaFree(h->sm_arrivals);
   delete h;
   return BMI_OK;
 }
@@ -1577,7 +1371,7 @@ extern "C" int bmi_env_sample_init(bmi_env* h, uint64_t seed, uint64_t* counter,
 extern "C" int bmi_env_step(bmi_env* h, const float* actions, float* obs, float* ag, float* reward, float* success,
                             bmi_stream_t stream) {
   BMI_REQUIRE(h && actions && obs && ag, "bmi_env_step: null pointer");
-  env_step_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), as_stream(stream)>>>(h->model_dev, h->ep, h->n_envs, h->sm_arrivals, h->state_dev,
+  env_step_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), as_stream(stream)>>>(h->model_dev, h->ep, h->n_envs, h->state_dev,
                                                                                           actions, obs, ag, reward, success);
   BMI_LAUNCHED();
   return BMI_OK;
@@ -1637,7 +1431,7 @@ extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream
   }
   ra.init = a->init; ra.obs = a->obs; ra.ag = a->ag; ra.g = a->g; ra.success = a->success;
   cudaStream_t st = as_stream(stream);
-  rollout_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->ep, h->n_envs, h->sm_arrivals, h->state_dev, ra);
+  rollout_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->ep, h->n_envs, h->state_dev, ra);
   BMI_LAUNCHED();
   if (a->explore) {
     advance_counter_kernel3<<<1, 1, 0, st>>>(a->counter, (uint64_t)a->T * (uint64_t)h->n_envs);

@@ -36,7 +36,7 @@ for rep in range(2):
     out = np.zeros((8192, 8), dtype=np.uint64)
     dbg(out.ctypes.data_as(ctypes.c_void_p), out.size, 0)
     out = out[:n].astype(np.float64)
-    names = ["policy", "ik+begin", "pre", "solver wait", "post", "iters", "substeps@150", "contacts"]
+    names = ["policy", "ik+begin", "pre", "solve+integrate", "(unused)", "iters", "substeps@150", "contacts"]
     tot = out[:, :5].sum(1)
     print("rollout %d: %.1f ms (%.0f env-steps/s); per-env busy cycles: median %.3g max %.3g (=%.1f ms at 1.965 GHz)" % (
         rep, ms, n * T / ms * 1e3, np.median(tot), tot.max(), tot.max() / 1.965e6))
@@ -50,4 +50,4 @@ for rep in range(2):
     for e_ in slow:
         print("  slow env %5d: total %.3g  " % (e_, tot[e_]) + " ".join("%s=%.0f" % (nm, out[e_, k] / nsub) for k, nm in enumerate(names)))
     wait_per_it = out[:, 3] / np.maximum(out[:, 5], 1)
-    print("  solver wait cycles per iteration: median %.0f  p90 %.0f  max %.0f" % (np.median(wait_per_it), np.percentile(wait_per_it, 90), wait_per_it.max()))
+    print("  solve cycles per iteration: median %.0f  p90 %.0f  max %.0f" % (np.median(wait_per_it), np.percentile(wait_per_it, 90), wait_per_it.max()))
