@@ -28,12 +28,24 @@ constexpr int EE = 8;          // right_hand2
 constexpr int MAXC = 9;        // contacts per sub-step (one solver lane each)
 constexpr int MAXA = 6;        // ... of which at most 6 involve an arm link
 constexpr int MAXR = 3 * MAXC; // contact rows: normal + two friction directions per contact
-constexpr int STAGED = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;  // floats staged by TMA
+constexpr int STAGED = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;  // floats staged by TMA (reset kernel: joint tree only)
+constexpr int STAGED_FULL = 1408;  // env kernels stage the WHOLE blob (joint tree + collision polytopes); capacity in floats
 constexpr int HID = 256;         // hidden width of the actor (models.py:15-17)
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef BMI_BLOCKS_PER_SM
 #define BMI_BLOCKS_PER_SM 1
 #endif
+#ifndef BMI_CONTACT_UNROLL
+#define BMI_CONTACT_UNROLL 1   // solver contact loops: 1 = rolled (the unrolled body thrashes the 6 KB L0 I-cache: measured 25 % slower)
+#endif
+constexpr int kContactUnroll = BMI_CONTACT_UNROLL;
+#ifndef BMI_SOLVE_SINGLE_VARIANT
+#define BMI_SOLVE_SINGLE_VARIANT 0
+#endif
+#ifndef BMI_MOTOR_UNROLL
+#define BMI_MOTOR_UNROLL 3
+#endif
+constexpr int kMotorUnroll = BMI_MOTOR_UNROLL;
 #ifndef BMI_ENVS_PER_BLOCK
 #define BMI_ENVS_PER_BLOCK 28
 #endif
@@ -78,9 +90,18 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
   float S[(MAXR + 1) * SS];
   union {
     struct {
-      float Rl[NL][9];
       union {
-        struct { float L[NL * NL], tauw[NL + 1][NL]; };   // mass matrix / Cholesky factor, per-lane RNEA rows
+        float Rl[NL][9];            // local joint rotations (fk only)
+        struct {                    // joint_space_dynamics scratch
+          union {
+            struct { float cm[NL], cc[NL][3], cI[NL][6]; };           // subtree mass / COM / inertia (mass matrix)
+            struct { float w[NL][3], al[NL][3], a[NL][3], vo[NL][3]; };  // link velocities / accelerations (bias)
+          };
+          float Nk[NL][3], Fk[NL][3];
+        } x;
+      };
+      union {
+        struct { float L[NL * NL], Iw[NL][6]; };          // mass matrix / Cholesky factor, world link inertias
         struct { float A[NL * NL], b[NL]; } ik;           // IK scratch (the IK runs before the sub-steps)
       };
     } dyn;                                                // live from fk to the end of contact generation
@@ -145,12 +166,11 @@ __device__ __forceinline__ void sincos_compact(float x, float* sn, float* cs) {
 
 // ---- TMA staging of the joint tree ---------------------------------------------------------
 __device__ __forceinline__ void stage_model(float* model_s, unsigned long long* mbar_s,
-                                            const float* __restrict__ model_g, int tid) {
+                                            const float* __restrict__ model_g, int tid, unsigned bytes) {
   const int lane = tid;  // thread 0 of the block issues the copy; every thread of every warp waits on the barrier
   const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_s);
   const unsigned dst = (unsigned)__cvta_generic_to_shared(model_s);
-  constexpr unsigned bytes = STAGED * sizeof(float);
-  static_assert(bytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+  // bytes: a multiple of 16 (TMA bulk copies move 16-byte units)
   if (lane == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -219,81 +239,166 @@ __device__ __noinline__ void fk(Smem& s, const float* q, int lane) {
   __syncwarp();
 }
 
-// ---- recursive Newton-Euler, one independent sweep per lane ------------------------------------
-// tau_j = z_j . sum_{k in subtree(j)} [ N_k + (c_k - p_j) x F_k ]   (accumulated pairwise so that no
-// per-link force arrays are needed; the tree topology is a compile-time constant).
-// Kept as a compact runtime loop (not unrolled): the kernel is instruction-fetch sensitive (profiles/r01_*).
-__device__ __noinline__ void rnea_lane(const Smem& s, bool is_bias, int unit, float gz, float kl, float ka,
-                                       float* tau) {  // tau: 9 floats in shared memory, private to this lane
-  constexpr bool kBias = true;  // the velocity terms are evaluated by every sweep (zeros for the unit sweeps)
-  float w[3] = {0, 0, 0}, al[3] = {0, 0, 0}, a[3] = {0, 0, -gz}, vo[3] = {0, 0, 0};
-  float w6[3] = {0, 0, 0}, al6[3] = {0, 0, 0}, a6[3] = {0, 0, 0}, vo6[3] = {0, 0, 0};
-  for (int j = 0; j < NL; ++j) tau[j] = 0.f;
+// ---- joint-space dynamics: mass matrix by composite rigid bodies, bias by one recursive Newton-Euler pass ---------
+// Same quantities as the oracle's rnea() calls (oracle/bmi_physics_oracle.c: the mass matrix is ten RNEA sweeps there);
+// here the work is spread over the warp instead of repeated per lane:
+//   M_jk = z_j . [ Ic_k z_k + (cc_k - p_j) x mc_k (z_k x (cc_k - p_k)) ]   for j on the path base -> k
+// (mc, cc, Ic: mass, centre of mass and inertia about it of the subtree hanging off joint k), and
+//   bias_j = z_j . sum_{l in subtree(j)} [ N_l + (c_l - p_j) x F_l ]
+// with the per-link wrenches F_l, N_l (velocity, gravity and Bullet link-damping terms) evaluated one link per lane
+// after a single serial pass for the link velocities / accelerations.
+__device__ __forceinline__ void sym_mat_vec(float* o, const float* I6, const float* v) {  // I6: xx xy xz yy yz zz
+  const float x = I6[0] * v[0] + I6[1] * v[1] + I6[2] * v[2], y = I6[1] * v[0] + I6[3] * v[1] + I6[4] * v[2],
+              z = I6[2] * v[0] + I6[4] * v[1] + I6[5] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+
+__device__ __noinline__ void joint_space_dynamics(Smem& s, float gz, float kl, float ka, int lane) {
+  auto& X = s.dyn.x;
+  // (1) world inertia of every link about its own COM, R diag(I) R^T: lane = (link, component)
+  for (int t = lane; t < NL * 6; t += 32) {
+    const int i = t / 6, ci = t - 6 * i;
+    const int a = ci < 3 ? 0 : (ci < 5 ? 1 : 2), b = ci < 3 ? ci : (ci < 5 ? ci - 2 : 2);
+    const float* R = s.R[i];
+    const float* I = LK(s, i) + ML_INERTIA;
+    s.dyn.Iw[i][ci] = R[3 * a] * I[0] * R[3 * b] + R[3 * a + 1] * I[1] * R[3 * b + 1] + R[3 * a + 2] * I[2] * R[3 * b + 2];
+  }
+  // (2) mass and centre of mass of every subtree: lane = joint
+  if (lane < NL) {
+    float m = 0.f, h[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
-  for (int i = 0; i < NL; ++i) {
-    const int pa = parent_of(i);
-    if (i == 7 || i == 8) {  // fingers hang off link 6
+    for (int l = lane; l < NL; ++l) {
+      if (!is_ancestor_or_self(lane, l)) continue;
+      const float ml = LK(s, l)[ML_MASS];
+      m += ml;
+      h[0] = fmaf(ml, s.c[l][0], h[0]); h[1] = fmaf(ml, s.c[l][1], h[1]); h[2] = fmaf(ml, s.c[l][2], h[2]);
+    }
+    const float im = 1.f / m;
+    X.cm[lane] = m;
+    X.cc[lane][0] = h[0] * im; X.cc[lane][1] = h[1] * im; X.cc[lane][2] = h[2] * im;
+  }
+  __syncwarp();
+  // (3) inertia of every subtree about its centre of mass (parallel-axis sums, all terms positive): lane = (joint, comp)
+  for (int t = lane; t < NL * 6; t += 32) {
+    const int j = t / 6, ci = t - 6 * j;
+    const int a = ci < 3 ? 0 : (ci < 5 ? 1 : 2), b = ci < 3 ? ci : (ci < 5 ? ci - 2 : 2);
+    const float c0 = X.cc[j][0], c1 = X.cc[j][1], c2 = X.cc[j][2];
+    float acc = 0.f;
+#pragma unroll 1
+    for (int l = j; l < NL; ++l) {
+      if (!is_ancestor_or_self(j, l)) continue;
+      const float d0 = s.c[l][0] - c0, d1 = s.c[l][1] - c1, d2 = s.c[l][2] - c2;
+      const float da = a == 0 ? d0 : (a == 1 ? d1 : d2), db = b == 0 ? d0 : (b == 1 ? d1 : d2);
+      const float dd = a == b ? d0 * d0 + d1 * d1 + d2 * d2 : 0.f;
+      acc += s.dyn.Iw[l][ci] + LK(s, l)[ML_MASS] * (dd - da * db);
+    }
+    X.cI[j][ci] = acc;
+  }
+  __syncwarp();
+  // (4) wrench of subtree k under a unit acceleration of joint k: lane = k
+  if (lane < NL) {
+    const float zk[3] = {s.z[lane][0], s.z[lane][1], s.z[lane][2]};
+    const float r[3] = {X.cc[lane][0] - s.p[lane][0], X.cc[lane][1] - s.p[lane][1], X.cc[lane][2] - s.p[lane][2]};
+    float N[3], ak[3];
+    sym_mat_vec(N, X.cI[lane], zk);
+    cross3(ak, zk, r);
+    const float m = X.cm[lane];
+    X.Nk[lane][0] = N[0]; X.Nk[lane][1] = N[1]; X.Nk[lane][2] = N[2];
+    X.Fk[lane][0] = m * ak[0]; X.Fk[lane][1] = m * ak[1]; X.Fk[lane][2] = m * ak[2];
+  }
+  __syncwarp();
+  // (5) lower triangle of M: lane = pair (k, j <= k)
+  for (int t = lane; t < NL * (NL + 1) / 2; t += 32) {
+    const int k = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15) + (t >= 21) + (t >= 28) + (t >= 36);
+    const int j = t - k * (k + 1) / 2;
+    float v = 0.f;
+    if (is_ancestor_or_self(j, k)) {
+      const float r[3] = {X.cc[k][0] - s.p[j][0], X.cc[k][1] - s.p[j][1], X.cc[k][2] - s.p[j][2]};
+      float m[3];
+      cross3(m, r, X.Fk[k]);
+      v = s.z[j][0] * (X.Nk[k][0] + m[0]) + s.z[j][1] * (X.Nk[k][1] + m[1]) + s.z[j][2] * (X.Nk[k][2] + m[2]);
+    }
+    s.dyn.L[k * NL + j] = v;
+  }
+  __syncwarp();
+  // (6) link velocities and accelerations (zero joint accelerations): one serial pass down the tree
+  if (lane == 0) {
+    float w[3] = {0.f, 0.f, 0.f}, al[3] = {0.f, 0.f, 0.f}, a[3] = {0.f, 0.f, -gz}, vo[3] = {0.f, 0.f, 0.f};
+    float w6[3], al6[3], a6[3], vo6[3];
+#pragma unroll 1
+    for (int i = 0; i < NL; ++i) {
+      const int pa = parent_of(i);
+      if (i == 7 || i == 8) {  // fingers hang off link 6
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { w[k] = w6[k]; al[k] = al6[k]; a[k] = a6[k]; vo[k] = vo6[k]; }
-    }
-    float t[3], t2[3];
-    if (pa >= 0) {
-      float r[3] = {s.p[i][0] - s.p[pa][0], s.p[i][1] - s.p[pa][1], s.p[i][2] - s.p[pa][2]};
-      if (kBias) { cross3(t, w, r); vo[0] += t[0]; vo[1] += t[1]; vo[2] += t[2]; }
-      cross3(t, al, r);
-      a[0] += t[0]; a[1] += t[1]; a[2] += t[2];
-      if (kBias) { cross3(t, w, r); cross3(t2, w, t); a[0] += t2[0]; a[1] += t2[1]; a[2] += t2[2]; }
-    }
-    const float qdi = is_bias ? s.qd[i] : 0.f;
-    const float qddi = (!is_bias && unit == i) ? 1.f : 0.f;
-    const float* zi = s.z[i];
-    if (kBias) { cross3(t, w, zi); al[0] += qdi * t[0]; al[1] += qdi * t[1]; al[2] += qdi * t[2]; }
-    al[0] += qddi * zi[0]; al[1] += qddi * zi[1]; al[2] += qddi * zi[2];
-    if (kBias) { w[0] += qdi * zi[0]; w[1] += qdi * zi[1]; w[2] += qdi * zi[2]; }
-    if (i == 6) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { w6[k] = w[k]; al6[k] = al[k]; a6[k] = a[k]; vo6[k] = vo[k]; }
-    }
-    const float* lk = LK(s, i);
-    const float mass = lk[ML_MASS];
-    float rc[3] = {s.c[i][0] - s.p[i][0], s.c[i][1] - s.p[i][1], s.c[i][2] - s.p[i][2]};
-    float ac[3];
-    cross3(t, al, rc);
-    ac[0] = a[0] + t[0]; ac[1] = a[1] + t[1]; ac[2] = a[2] + t[2];
-    float F[3], N[3];
-    if (kBias) {
-      cross3(t, w, rc); cross3(t2, w, t);
-      ac[0] += t2[0]; ac[1] += t2[1]; ac[2] += t2[2];
-      float vc[3] = {vo[0] + t[0], vo[1] + t[1], vo[2] + t[2]};
-      const float vn = sqrtf(dot3(vc, vc));
-      const float kd = mass * (kl + kl * vn);
-      F[0] = mass * ac[0] + kd * vc[0]; F[1] = mass * ac[1] + kd * vc[1]; F[2] = mass * ac[2] + kd * vc[2];
-    } else {
-      F[0] = mass * ac[0]; F[1] = mass * ac[1]; F[2] = mass * ac[2];
-    }
-    {
-      float ll[3], tl[3];
-      matT_vec(ll, s.R[i], al);
-      tl[0] = lk[ML_INERTIA] * ll[0]; tl[1] = lk[ML_INERTIA + 1] * ll[1]; tl[2] = lk[ML_INERTIA + 2] * ll[2];
-      mat_vec(N, s.R[i], tl);
-      if (kBias) {
-        float wl[3], Iw[3];
-        matT_vec(wl, s.R[i], w);
-        tl[0] = lk[ML_INERTIA] * wl[0]; tl[1] = lk[ML_INERTIA + 1] * wl[1]; tl[2] = lk[ML_INERTIA + 2] * wl[2];
-        mat_vec(Iw, s.R[i], tl);
-        cross3(t, w, Iw);
-        const float wn = sqrtf(dot3(w, w));
-        const float kk = ka + ka * wn;
-        N[0] += t[0] + kk * Iw[0]; N[1] += t[1] + kk * Iw[1]; N[2] += t[2] + kk * Iw[2];
+        for (int k = 0; k < 3; ++k) { w[k] = w6[k]; al[k] = al6[k]; a[k] = a6[k]; vo[k] = vo6[k]; }
       }
-    }
-#pragma unroll 1
-    for (int j = i; j >= 0; j = parent_of(j)) {  // every joint on the path base -> link i feels link i's wrench
-      float r[3] = {s.c[i][0] - s.p[j][0], s.c[i][1] - s.p[j][1], s.c[i][2] - s.p[j][2]};
-      cross3(t, r, F);
-      tau[j] += s.z[j][0] * (N[0] + t[0]) + s.z[j][1] * (N[1] + t[1]) + s.z[j][2] * (N[2] + t[2]);
+      if (pa >= 0) {
+        const float r[3] = {s.p[i][0] - s.p[pa][0], s.p[i][1] - s.p[pa][1], s.p[i][2] - s.p[pa][2]};
+        float t[3], t2[3];
+        cross3(t, w, r);
+        vo[0] += t[0]; vo[1] += t[1]; vo[2] += t[2];
+        cross3(t2, w, t);
+        cross3(t, al, r);
+        a[0] += t[0] + t2[0]; a[1] += t[1] + t2[1]; a[2] += t[2] + t2[2];
+      }
+      const float qdi = s.qd[i];
+      const float zi[3] = {s.z[i][0], s.z[i][1], s.z[i][2]};
+      {
+        float t[3];
+        cross3(t, w, zi);
+        al[0] = fmaf(qdi, t[0], al[0]); al[1] = fmaf(qdi, t[1], al[1]); al[2] = fmaf(qdi, t[2], al[2]);
+        w[0] = fmaf(qdi, zi[0], w[0]); w[1] = fmaf(qdi, zi[1], w[1]); w[2] = fmaf(qdi, zi[2], w[2]);
+      }
+      if (i == 6) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { w6[k] = w[k]; al6[k] = al[k]; a6[k] = a[k]; vo6[k] = vo[k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { X.w[i][k] = w[k]; X.al[i][k] = al[k]; X.a[i][k] = a[k]; X.vo[i][k] = vo[k]; }
     }
   }
+  __syncwarp();
+  // (7) wrench of every link, moment taken about the world origin: lane = link
+  if (lane < NL) {
+    const int i = lane;
+    const float w[3] = {X.w[i][0], X.w[i][1], X.w[i][2]}, al[3] = {X.al[i][0], X.al[i][1], X.al[i][2]};
+    const float ci[3] = {s.c[i][0], s.c[i][1], s.c[i][2]};
+    const float rc[3] = {ci[0] - s.p[i][0], ci[1] - s.p[i][1], ci[2] - s.p[i][2]};
+    const float mass = LK(s, i)[ML_MASS];
+    float t[3], t2[3], t3[3];
+    cross3(t, w, rc);    // velocity of the COM relative to the link origin
+    cross3(t2, w, t);
+    cross3(t3, al, rc);
+    const float ac[3] = {X.a[i][0] + t3[0] + t2[0], X.a[i][1] + t3[1] + t2[1], X.a[i][2] + t3[2] + t2[2]};
+    const float vc[3] = {X.vo[i][0] + t[0], X.vo[i][1] + t[1], X.vo[i][2] + t[2]};
+    const float kd = mass * (kl + kl * sqrtf(dot3(vc, vc)));
+    const float F[3] = {mass * ac[0] + kd * vc[0], mass * ac[1] + kd * vc[1], mass * ac[2] + kd * vc[2]};
+    float Iw_w[3], N[3];
+    sym_mat_vec(Iw_w, s.dyn.Iw[i], w);
+    sym_mat_vec(N, s.dyn.Iw[i], al);
+    cross3(t, w, Iw_w);
+    const float kk = ka + ka * sqrtf(dot3(w, w));
+    cross3(t2, ci, F);
+    X.Fk[i][0] = F[0]; X.Fk[i][1] = F[1]; X.Fk[i][2] = F[2];
+    X.Nk[i][0] = N[0] + t[0] + kk * Iw_w[0] + t2[0];
+    X.Nk[i][1] = N[1] + t[1] + kk * Iw_w[1] + t2[1];
+    X.Nk[i][2] = N[2] + t[2] + kk * Iw_w[2] + t2[2];
+  }
+  __syncwarp();
+  // (8) bias torque of joint j: z_j . (sum of subtree moments about the origin - p_j x sum of subtree forces)
+  if (lane < NL) {
+    float FS[3] = {0.f, 0.f, 0.f}, NS[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int l = lane; l < NL; ++l) {
+      if (!is_ancestor_or_self(lane, l)) continue;
+      FS[0] += X.Fk[l][0]; FS[1] += X.Fk[l][1]; FS[2] += X.Fk[l][2];
+      NS[0] += X.Nk[l][0]; NS[1] += X.Nk[l][1]; NS[2] += X.Nk[l][2];
+    }
+    float t[3];
+    cross3(t, s.p[lane], FS);
+    s.bias[lane] = s.z[lane][0] * (NS[0] - t[0]) + s.z[lane][1] * (NS[1] - t[1]) + s.z[lane][2] * (NS[2] - t[2]);
+  }
+  __syncwarp();
 }
 
 // Cholesky of the 9x9 SPD matrix in s.L (lower, in place, reciprocal diagonal); lanes cooperate per column.
@@ -454,18 +559,18 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
     push_contacts(s, m, lane, -1, 1, bvx, up, d, ep.bmu * P(s, MP_MU_TABLE));
   }
   const int ns = (int)P(s, MP_N_SHAPES);
-  const float* shapes = model_g + (int)P(s, MP_SHAPES_OFF);
-  const float* pool = model_g + (int)P(s, MP_POOL_OFF);
+  const float* shapes = s.model + (int)P(s, MP_SHAPES_OFF);   // staged in shared memory with the joint tree
+  const float* pool = s.model + (int)P(s, MP_POOL_OFF);
   const float brad = sqrtf(ep.bh[0] * ep.bh[0] + ep.bh[1] * ep.bh[1] + ep.bh[2] * ep.bh[2]);
   for (int si = 0; si < ns; ++si) {
     const float* sh = shapes + si * BMI_SHAPE_STRIDE;
-    const int l = (int)__ldg(sh + MS_LINK), nv = (int)__ldg(sh + MS_NVERTS), np = (int)__ldg(sh + MS_NPLANES);
-    const float* verts = pool + (int)__ldg(sh + MS_VERT_OFF);
-    const float* planes = pool + (int)__ldg(sh + MS_PLANE_OFF);
-    const float smu = __ldg(sh + MS_MU);
+    const int l = (int)(*(sh + MS_LINK)), nv = (int)(*(sh + MS_NVERTS)), np = (int)(*(sh + MS_NPLANES));
+    const float* verts = pool + (int)(*(sh + MS_VERT_OFF));
+    const float* planes = pool + (int)(*(sh + MS_PLANE_OFF));
+    const float smu = (*(sh + MS_MU));
     float wv[3] = {0, 0, 0};
     if (lane < nv) {
-      float lv[3] = {__ldg(verts + 3 * lane), __ldg(verts + 3 * lane + 1), __ldg(verts + 3 * lane + 2)};
+      float lv[3] = {(*(verts + 3 * lane)), (*(verts + 3 * lane + 1)), (*(verts + 3 * lane + 2))};
       mat_vec(wv, s.R[l], lv);
       wv[0] += s.p[l][0]; wv[1] += s.p[l][1]; wv[2] += s.p[l][2];
     }
@@ -475,10 +580,10 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
       push_contacts(s, m, lane, l, 0, wv, up, d, smu * P(s, MP_MU_TABLE));
     }
     // broadphase: bounding spheres
-    float lc[3] = {__ldg(sh + MS_SPHERE_C), __ldg(sh + MS_SPHERE_C + 1), __ldg(sh + MS_SPHERE_C + 2)}, cw[3];
+    float lc[3] = {(*(sh + MS_SPHERE_C)), (*(sh + MS_SPHERE_C + 1)), (*(sh + MS_SPHERE_C + 2))}, cw[3];
     mat_vec(cw, s.R[l], lc);
     float dd[3] = {s.bp[0] - cw[0] - s.p[l][0], s.bp[1] - cw[1] - s.p[l][1], s.bp[2] - cw[2] - s.p[l][2]};
-    if (sqrtf(dot3(dd, dd)) > __ldg(sh + MS_SPHERE_R) + brad + block_margin) continue;  // uniform
+    if (sqrtf(dot3(dd, dd)) > (*(sh + MS_SPHERE_R)) + brad + block_margin) continue;  // uniform
     // candidates: lanes 0..7 = block vertex vs hull planes, lanes 8..8+nv-1 = hull vertex vs block box
     float d = 3.0e38f, nrm[3] = {0, 0, 0}, x[3] = {0, 0, 0};
     bool valid = false;
@@ -489,11 +594,11 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
       int bpi = 0;
 #pragma unroll 2
       for (int pi = 0; pi < np; ++pi) {
-        const float4 pl = __ldg(reinterpret_cast<const float4*>(planes) + pi);
+        const float4 pl = reinterpret_cast<const float4*>(planes)[pi];
         const float sd = pl.x * xl[0] + pl.y * xl[1] + pl.z * xl[2] + pl.w;
         if (sd > best) { best = sd; bpi = pi; }
       }
-      const float4 pl = __ldg(reinterpret_cast<const float4*>(planes) + bpi);
+      const float4 pl = reinterpret_cast<const float4*>(planes)[bpi];
       float ln[3] = {pl.x, pl.y, pl.z};
       mat_vec(nrm, s.R[l], ln);
       d = best; valid = true;
@@ -543,27 +648,7 @@ __device__ __forceinline__ void plane_space(const float* n, float* p, float* q) 
 __device__ __noinline__ void substep_dynamics(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, int lane) {
   const float dt = P(s, MP_DT), gz = P(s, MP_GRAVITY), kl = P(s, MP_LIN_DAMP), ka = P(s, MP_ANG_DAMP);
   fk(s, s.q, lane);
-  {  // mass matrix columns (lanes 0..8) and bias (lane 9)
-    if (lane <= NL) {  // one code path for all ten sweeps (no divergence): unit lanes see zero velocity / gravity
-      const bool is_bias = lane == NL;
-      float* tau = s.dyn.tauw[lane];
-      rnea_lane(s, is_bias, lane, is_bias ? gz : 0.f, is_bias ? kl : 0.f, is_bias ? ka : 0.f, tau);
-      for (int i = 0; i < NL; ++i) {
-        if (is_bias) s.bias[i] = tau[i];
-        else s.dyn.L[i * NL + lane] = tau[i];
-      }
-    }
-  }
-  __syncwarp();
-  if (lane < NL) {  // symmetrise (lower triangle is what Cholesky reads)
-    float v[NL];
-#pragma unroll
-    for (int j = 0; j < NL; ++j) v[j] = 0.5f * (s.dyn.L[lane * NL + j] + s.dyn.L[j * NL + lane]);
-    __syncwarp(0x1ff);
-#pragma unroll
-    for (int j = 0; j < NL; ++j) s.dyn.L[lane * NL + j] = v[j];
-  }
-  __syncwarp();
+  joint_space_dynamics(s, gz, kl, ka, lane);
   chol9(s.dyn.L, lane);
   // M^-1 columns (lanes 0..8) and unconstrained acceleration (lane 9)
   if (lane <= NL) {
@@ -606,6 +691,14 @@ __device__ __forceinline__ float lds_f(unsigned addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
+}
+
+// MUFU.RSQ without the denormal-range rescaling of rsqrtf (the argument is a squared impulse norm well inside the
+// normal range whenever the result is used)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 #ifdef BMI_PROF
@@ -746,93 +839,96 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   }
   __syncwarp();
   // ---- owner lanes pick up their rows' scalars; per-lane coefficient addresses --------------------------------------
+  // joint events (source joint j):   coefficient k of this lane at ja + 4 j + k * SS * 4
+  // contact events (source row x):   coefficient k of this lane at ca + x * SS * 4 + 4 k
+  // Only contact lanes own three variables; for the others k = 1, 2 read in-bounds don't-care words into v1 / v2,
+  // which they never use (that keeps ONE address register per event type and immediate offsets for k).
   const unsigned s_base = (unsigned)__cvta_generic_to_shared(s.S);
-  const unsigned zero_row = s_base + MAXR * SS * 4u;
-  // joint events (source joint j): coefficient k of this lane at ja_k + 4 j
-  // contact events (source row x): coefficient k of this lane at ca_k + x * SS * 4
-  unsigned ja0 = zero_row, ja1 = zero_row, ja2 = zero_row, ca0 = s_base, ca1 = s_base, ca2 = s_base;
+  unsigned ja = s_base + MAXR * SS * 4u, ca = s_base;   // default: the zero row / column 0 (idle lanes)
   const int myc = lane - LANE_CT;
   if (lane < NL) {
-    ja0 = ja1 = ja2 = (unsigned)__cvta_generic_to_shared(s.Minv) + (unsigned)lane * (MS * 4u);
-    ca0 = ca1 = ca2 = s_base + (unsigned)lane * 4u;
+    ja = (unsigned)__cvta_generic_to_shared(s.Minv) + (unsigned)lane * (MS * 4u);
+    ca = s_base + (unsigned)lane * 4u;
   } else if (lane < LANE_BLK + 6) {
-    ca0 = ca1 = ca2 = s_base + (unsigned)lane * 4u;   // columns 9..14
+    ca = s_base + (unsigned)lane * 4u;   // columns 9..14
   } else if (myc >= 0 && myc < nc) {
     const float4 a = s.rows.sc[3 * myc], b = s.rows.sc[3 * myc + 1], c = s.rows.sc[3 * myc + 2];
     inv0 = a.x; rhs0 = a.y; dg0 = a.z; mu = a.w;
     inv1 = b.x; rhs1 = b.y; dg1 = b.z;
     inv2 = c.x; rhs2 = c.y; dg2 = c.z;
-    ja0 = s_base + (unsigned)(3 * myc) * (SS * 4u);
-    ja1 = ja0 + SS * 4u; ja2 = ja1 + SS * 4u;
-    ca0 = s_base + (unsigned)(SCOL_CT + 3 * myc) * 4u;
-    ca1 = ca0 + 4u; ca2 = ca0 + 8u;
+    ja = s_base + (unsigned)(3 * myc) * (SS * 4u);
+    ca = s_base + (unsigned)(SCOL_CT + 3 * myc) * 4u;
   }
   const int max_it = (int)P(s, MP_SOLVER_ITERS);
   const float thresh = P(s, MP_RESIDUAL_THRESH);
   int it = 0;
-  // one joint-source update: every lane adds its coefficient x d
-#define BMI_JOINT_EVENT(joff, dj)                                                         \
+  // one joint-source update: every lane adds its coefficient x d (contact lanes: all three rows, only when some
+  // contact touches the arm — otherwise their coefficients are zero)
+#define BMI_JOINT_EVENT(ARM, joff, dj)                                                    \
   do {                                                                                    \
-    const float c0_ = lds_f(ja0 + (joff));                                                \
-    if (has_arm) {                                                                        \
-      const float c1_ = lds_f(ja1 + (joff)), c2_ = lds_f(ja2 + (joff));                   \
+    const float c0_ = lds_f(ja + (joff));                                                 \
+    if (ARM) {                                                                            \
+      const float c1_ = lds_f(ja + (joff) + SS * 4u), c2_ = lds_f(ja + (joff) + 2u * SS * 4u); \
       v1 = fmaf(c1_, (dj), v1); v2 = fmaf(c2_, (dj), v2);                                 \
     }                                                                                     \
     v0 = fmaf(c0_, (dj), v0);                                                             \
   } while (0)
+  // motors (J = e_j, bounds +-max_imp), then violated joint limits (J = +-e_j, bounds [0, hi])
+#define BMI_JOINT_ROWS(ARM)                                                               \
+  do {                                                                                    \
+    _Pragma("unroll (kMotorUnroll)")                                                      \
+    for (int j = 0; j < NL; ++j) {                                                        \
+      const float cand = fminf(fmaxf(lam0 + fmaf(-v0, inv0, rhs0), -max_imp), max_imp);   \
+      const float d = cand - lam0;                                                        \
+      const float dj = __shfl_sync(FULL, d, j);                                           \
+      if (lane == j) { lam0 = cand; dl0 = d; }                                            \
+      BMI_JOINT_EVENT(ARM, 4u * j, dj);                                                   \
+    }                                                                                     \
+    for (unsigned m = limit_mask; m; m &= m - 1u) {                                       \
+      const int j = __ffs(m) - 1;                                                         \
+      const float cand = fminf(fmaxf(lam1 + fmaf(-v0, inv1, rhs1), 0.f), lim_hi);         \
+      const float d = cand - lam1;                                                        \
+      const float dj = __shfl_sync(FULL, d * lsgn, j);                                    \
+      if (lane == j) { lam1 = cand; dl1 = d; }                                            \
+      BMI_JOINT_EVENT(ARM, 4u * (unsigned)j, dj);                                         \
+    }                                                                                     \
+  } while (0)
 #pragma unroll 1
   while (true) {
-    // ---- motors: J = e_j, bounds +-max_imp ----------------------------------------------------------------------
-#pragma unroll
-    for (int j = 0; j < NL; ++j) {
-      const float cand = fminf(fmaxf(lam0 + fmaf(-v0, inv0, rhs0), -max_imp), max_imp);
+#if BMI_SOLVE_SINGLE_VARIANT
+    BMI_JOINT_ROWS(true);
+#else
+    if (has_arm) BMI_JOINT_ROWS(true); else BMI_JOINT_ROWS(false);
+#endif
+    // ---- contact normals (unrolled over the contact slot: static shuffle lane, owner test and table offset) -------
+#pragma unroll (kContactUnroll)
+    for (int c = 0; c < MAXC; ++c) {
+      if (c >= nc) break;   // uniform
+      const unsigned a = ca + (unsigned)c * (3u * SS * 4u);
+      const float c0 = lds_f(a), c1 = lds_f(a + 4u), c2 = lds_f(a + 8u);
+      const float cand = fmaxf(lam0 + fmaf(-v0, inv0, rhs0), 0.f);
       const float d = cand - lam0;
-      const float dj = __shfl_sync(FULL, d, j);
-      if (lane == j) { lam0 = cand; dl0 = d; }
-      BMI_JOINT_EVENT(4u * j, dj);
-    }
-    // ---- violated joint limits: J = +-e_j, bounds [0, hi] ---------------------------------------------------------
-    for (unsigned m = limit_mask; m; m &= m - 1u) {
-      const int j = __ffs(m) - 1;
-      const float cand = fminf(fmaxf(lam1 + fmaf(-v0, inv1, rhs1), 0.f), lim_hi);
-      const float d = cand - lam1;
-      const float dj = __shfl_sync(FULL, d * lsgn, j);
-      if (lane == j) { lam1 = cand; dl1 = d; }
-      BMI_JOINT_EVENT(4u * (unsigned)j, dj);
-    }
-    // ---- contact normals ------------------------------------------------------------------------------------------
-    {
-      unsigned a0 = ca0, a1 = ca1, a2 = ca2;
-#pragma unroll 1
-      for (int c = 0; c < nc; ++c) {
-        const float c0 = lds_f(a0), c1 = lds_f(a1), c2 = lds_f(a2);
-        const float cand = fmaxf(lam0 + fmaf(-v0, inv0, rhs0), 0.f);
-        const float d = cand - lam0;
-        const float dc = __shfl_sync(FULL, d, LANE_CT + c);
-        if (myc == c) { lam0 = cand; dl0 = d; }
-        v0 = fmaf(c0, dc, v0); v1 = fmaf(c1, dc, v1); v2 = fmaf(c2, dc, v2);
-        a0 += 3u * SS * 4u; a1 += 3u * SS * 4u; a2 += 3u * SS * 4u;
-      }
+      const float dc = __shfl_sync(FULL, d, LANE_CT + c);
+      if (myc == c) { lam0 = cand; dl0 = d; }
+      v0 = fmaf(c0, dc, v0); v1 = fmaf(c1, dc, v1); v2 = fmaf(c2, dc, v2);
     }
     // ---- friction cones -------------------------------------------------------------------------------------------
-    {
-      unsigned a0 = ca0 + SS * 4u, a1 = ca1 + SS * 4u, a2 = ca2 + SS * 4u;
-#pragma unroll 1
-      for (int c = 0; c < nc; ++c) {
-        const float p0 = lds_f(a0), p1 = lds_f(a1), p2 = lds_f(a2);
-        const float q0 = lds_f(a0 + SS * 4u), q1 = lds_f(a1 + SS * 4u), q2 = lds_f(a2 + SS * 4u);
-        const float lim = mu * lam0;
-        float sa = lam1 + fmaf(-v1, inv1, rhs1), sb = lam2 + fmaf(-v2, inv2, rhs2);
-        const float n2 = sa * sa + sb * sb;
-        const float sc = n2 > lim * lim ? lim * rsqrtf(n2) : 1.f;  // branch-free cone projection (x * 1 is exact)
-        sa *= sc; sb *= sc;
-        const float da = sa - lam1, db = sb - lam2;
-        const float dac = __shfl_sync(FULL, da, LANE_CT + c), dbc = __shfl_sync(FULL, db, LANE_CT + c);
-        if (myc == c) { lam1 = sa; lam2 = sb; dl1 = da; dl2 = db; }
-        v0 = fmaf(p0, dac, v0); v1 = fmaf(p1, dac, v1); v2 = fmaf(p2, dac, v2);
-        v0 = fmaf(q0, dbc, v0); v1 = fmaf(q1, dbc, v1); v2 = fmaf(q2, dbc, v2);
-        a0 += 3u * SS * 4u; a1 += 3u * SS * 4u; a2 += 3u * SS * 4u;
-      }
+#pragma unroll (kContactUnroll)
+    for (int c = 0; c < MAXC; ++c) {
+      if (c >= nc) break;   // uniform
+      const unsigned a = ca + (unsigned)c * (3u * SS * 4u) + SS * 4u;
+      const float p0 = lds_f(a), p1 = lds_f(a + 4u), p2 = lds_f(a + 8u);
+      const float q0 = lds_f(a + SS * 4u), q1 = lds_f(a + SS * 4u + 4u), q2 = lds_f(a + SS * 4u + 8u);
+      const float lim = mu * lam0;
+      float sa = lam1 + fmaf(-v1, inv1, rhs1), sb = lam2 + fmaf(-v2, inv2, rhs2);
+      const float n2 = sa * sa + sb * sb;
+      const float sc = n2 > lim * lim ? lim * rsqrt_fast(n2) : 1.f;  // branch-free cone projection (x * 1 is exact)
+      sa *= sc; sb *= sc;
+      const float da = sa - lam1, db = sb - lam2;
+      const float dac = __shfl_sync(FULL, da, LANE_CT + c), dbc = __shfl_sync(FULL, db, LANE_CT + c);
+      if (myc == c) { lam1 = sa; lam2 = sb; dl1 = da; dl2 = db; }
+      v0 = fmaf(p0, dac, v0); v1 = fmaf(p1, dac, v1); v2 = fmaf(p2, dac, v2);
+      v0 = fmaf(q0, dbc, v0); v1 = fmaf(q1, dbc, v1); v2 = fmaf(q2, dbc, v2);
     }
     // ---- residual: max over all rows of (impulse change x row diagonal)^2 ------------------------------------------
     const float r0 = dl0 * dg0, r1 = dl1 * dg1, r2 = dl2 * dg2;
@@ -841,6 +937,7 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
     ++it;
     if (resid <= thresh || it >= max_it) break;
   }
+#undef BMI_JOINT_ROWS
 #undef BMI_JOINT_EVENT
 #ifdef BMI_PROF
   if (lane == 0) s.prof_iters = it;
@@ -954,7 +1051,7 @@ __device__ __forceinline__ float goal_dist(const Smem& s) {
 }
 // ---- block layout ---------------------------------------------------------------------------------------------
 struct BlockSmem {
-  float model_s[STAGED];
+  float model_s[STAGED_FULL];
   unsigned long long mbar;
   int pad_[2];
   Smem sw[ENVW];
@@ -969,9 +1066,9 @@ PrintSize<sizeof(Smem)> print_smem_size;
 extern __shared__ __align__(16) unsigned char bmi_dyn_smem[];
 
 // Block prologue: stage the model (one TMA bulk copy, shared by the block's envs), point every env slot at it.
-__device__ __forceinline__ void block_begin(BlockSmem& bs, const float* __restrict__ model_g) {
+__device__ __forceinline__ void block_begin(BlockSmem& bs, const float* __restrict__ model_g, unsigned model_bytes) {
   if (threadIdx.x < ENVW) bs.sw[threadIdx.x].model = bs.model_s;
-  stage_model(bs.model_s, &bs.mbar, model_g, threadIdx.x);  // mbarrier-init fence + __syncthreads inside
+  stage_model(bs.model_s, &bs.mbar, model_g, threadIdx.x, model_bytes);  // mbarrier-init fence + __syncthreads inside
 }
 
 // clip, (pick: auto-grip), IK, motor set-points  (bmirobot_env_push_F.py:92-101) — one warp per env
@@ -1021,12 +1118,12 @@ __device__ __forceinline__ void env_step_warp(Smem& s, const EnvParams& ep, cons
 
 // ---- kernels ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
-env_step_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs,
+env_step_kernel(const float* __restrict__ model_g, unsigned model_bytes, EnvParams ep, int n_envs,
                 float* __restrict__ state, const float* __restrict__ actions, float* __restrict__ obs,
                 float* __restrict__ ag, float* __restrict__ reward, float* __restrict__ success) {
   BlockSmem& bs = *reinterpret_cast<BlockSmem*>(bmi_dyn_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  block_begin(bs, model_g);
+  block_begin(bs, model_g, model_bytes);
   const int e = blockIdx.x * ENVW + warp;
   if (e >= n_envs) return;  // whole warp
   Smem& s = bs.sw[warp];
@@ -1090,11 +1187,11 @@ __device__ __noinline__ Philox4 philox_explore(unsigned long long seed, unsigned
 }
 
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
-rollout_kernel(const float* __restrict__ model_g, EnvParams ep, int n_envs,
+rollout_kernel(const float* __restrict__ model_g, unsigned model_bytes, EnvParams ep, int n_envs,
                float* __restrict__ state, RolloutArgs ra) {
   BlockSmem& bs = *reinterpret_cast<BlockSmem*>(bmi_dyn_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  block_begin(bs, model_g);
+  block_begin(bs, model_g, model_bytes);
   const int e = blockIdx.x * ENVW + warp;
   if (e >= n_envs) return;  // whole warp
   Smem& s = bs.sw[warp];
@@ -1222,7 +1319,7 @@ env_reset_kernel(const float* __restrict__ model_g, int n_envs, float* __restric
   __shared__ Smem sw[RESET_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * RESET_WARPS + warp;
-  stage_model(model_s, &mbar_s, model_g, threadIdx.x);
+  stage_model(model_s, &mbar_s, model_g, threadIdx.x, STAGED * sizeof(float));
   if (e >= n_envs) return;
   Smem& s = sw[warp];
   if (lane == 0) s.model = model_s;
@@ -1287,6 +1384,7 @@ struct bmi_env {
   float* model_dev = nullptr;
   float* state_dev = nullptr;
   int64_t model_floats = 0;
+  unsigned model_bytes = 0;     // staged size: the blob rounded up to 16 bytes
 };
 
 extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const void* blob, int64_t bytes) {
@@ -1298,6 +1396,8 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   const int64_t n = bytes / 4;
   BMI_REQUIRE(b[MP_MAGIC] == BMI_MODEL_MAGIC && (int64_t)b[MP_TOTAL] == n && n <= BMI_MODEL_MAX_FLOATS,
               "bmi_env_create: model blob magic/size mismatch");
+  BMI_REQUIRE(n <= STAGED_FULL, "bmi_env_create: model blob (%lld floats) exceeds the shared-memory staging area (%d)",
+              (long long)n, STAGED_FULL);
   BMI_REQUIRE((int)b[MP_N_LINKS] == NL && (int)b[MP_EE_LINK] == EE && (int)b[MP_N_SHAPES] <= BMI_MAX_SHAPES &&
                   (int)b[MP_LINKS_OFF] == BMI_MODEL_HDR,
               "bmi_env_create: model does not match the compiled arm topology");
@@ -1328,12 +1428,14 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   h->ep.binertia[1] = mm * (lx * lx + lz * lz);
   h->ep.binertia[2] = mm * (lx * lx + ly * ly);
   h->model_floats = n;
-  if (cudaMalloc(&h->model_dev, n * sizeof(float)) != cudaSuccess ||
+  h->model_bytes = (unsigned)(((n * sizeof(float) + 15) / 16) * 16);
+  if (cudaMalloc(&h->model_dev, h->model_bytes) != cudaSuccess ||
       cudaMalloc(&h->state_dev, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)) != cudaSuccess) {
     set_error("bmi_env_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     bmi_env_destroy(h);
     return BMI_ERR_CUDA;
   }
+  BMI_CUDA_CHECK(cudaMemset(h->model_dev, 0, h->model_bytes));
   BMI_CUDA_CHECK(cudaMemcpy(h->model_dev, blob, n * sizeof(float), cudaMemcpyHostToDevice));
   BMI_CUDA_CHECK(cudaMemset(h->state_dev, 0, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)));
   *out = h;
@@ -1371,7 +1473,7 @@ extern "C" int bmi_env_sample_init(bmi_env* h, uint64_t seed, uint64_t* counter,
 extern "C" int bmi_env_step(bmi_env* h, const float* actions, float* obs, float* ag, float* reward, float* success,
                             bmi_stream_t stream) {
   BMI_REQUIRE(h && actions && obs && ag, "bmi_env_step: null pointer");
-  env_step_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), as_stream(stream)>>>(h->model_dev, h->ep, h->n_envs, h->state_dev,
+  env_step_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), as_stream(stream)>>>(h->model_dev, h->model_bytes, h->ep, h->n_envs, h->state_dev,
                                                                                           actions, obs, ag, reward, success);
   BMI_LAUNCHED();
   return BMI_OK;
@@ -1431,7 +1533,7 @@ extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream
   }
   ra.init = a->init; ra.obs = a->obs; ra.ag = a->ag; ra.g = a->g; ra.success = a->success;
   cudaStream_t st = as_stream(stream);
-  rollout_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->ep, h->n_envs, h->state_dev, ra);
+  rollout_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->model_bytes, h->ep, h->n_envs, h->state_dev, ra);
   BMI_LAUNCHED();
   if (a->explore) {
     advance_counter_kernel3<<<1, 1, 0, st>>>(a->counter, (uint64_t)a->T * (uint64_t)h->n_envs);
