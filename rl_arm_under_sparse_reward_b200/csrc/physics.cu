@@ -110,7 +110,7 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
   };
   float obs[BMI_OBS_DIM + BMI_GOAL_DIM];   // last observation + achieved goal (fused rollout)
   float qik[NL];
-  int prof_iters;
+  int prof_e;
 };
 
 struct EnvParams {
@@ -163,6 +163,20 @@ __device__ __forceinline__ void sincos_compact(float x, float* sn, float* cs) {
   *sn = (k & 2) ? -a : a;
   *cs = ((k + 1) & 2) ? -b : b;
 }
+
+#ifdef BMI_PROF
+// Debug build only (tools/prof_rollout_phases.py): per-env cycle counters of the fused rollout.
+__device__ unsigned long long g_prof[8192 * 8];
+#define PROF_T0() long long prof_t0 = clock64()
+#define PROF_ADD(e, k) do { const long long t1_ = clock64(); if (lane == 0 && (e) < 8192) g_prof[(e) * 8 + (k)] += (unsigned long long)(t1_ - prof_t0); prof_t0 = t1_; } while (0)
+#define PROF_CNT(e, k, v) do { if (lane == 0 && (e) < 8192) g_prof[(e) * 8 + (k)] += (unsigned long long)(v); } while (0)
+#define PROF_RESET() prof_t0 = clock64()
+#else
+#define PROF_T0()
+#define PROF_ADD(e, k)
+#define PROF_CNT(e, k, v)
+#define PROF_RESET()
+#endif
 
 // ---- TMA staging of the joint tree ---------------------------------------------------------
 __device__ __forceinline__ void stage_model(float* model_s, unsigned long long* mbar_s,
@@ -401,25 +415,31 @@ __device__ __noinline__ void joint_space_dynamics(Smem& s, float gz, float kl, f
   __syncwarp();
 }
 
-// Cholesky of the 9x9 SPD matrix in s.L (lower, in place, reciprocal diagonal); lanes cooperate per column.
+// Cholesky of the 9x9 SPD matrix in Lm (lower triangle valid; factor written back in place, reciprocal diagonal).
+// Lane i < 9 keeps row i in registers; column j is finished with one shuffle for the pivot and one per trailing row
+// (45 shuffles in all, no shared-memory round trips between columns).
 __device__ __noinline__ void chol9(float* Lm, int lane) {
-#pragma unroll 1
+  const int row = lane < NL ? lane : NL - 1;
+  float a[NL];
+#pragma unroll
+  for (int k = 0; k < NL; ++k) a[k] = Lm[row * NL + k];   // entries k > row are never used
+#pragma unroll
   for (int j = 0; j < NL; ++j) {
-    float d = 0.f;
-    if (lane == 0) {
-      d = Lm[j * NL + j];
-      for (int k = 0; k < j; ++k) d -= Lm[j * NL + k] * Lm[j * NL + k];
-      d = rsqrtf(fmaxf(d, 1e-20f));   // the diagonal stores 1 / L_jj: the solves multiply instead of divide
-      Lm[j * NL + j] = d;
+    const float pj = __shfl_sync(FULL, a[j], j);
+    const float d = rsqrtf(fmaxf(pj, 1e-20f));   // the diagonal stores 1 / L_jj: the solves multiply instead of divide
+    const float Lij = a[j] * d;
+    a[j] = lane == j ? d : Lij;
+#pragma unroll
+    for (int k = j + 1; k < NL; ++k) {
+      const float Lkj = __shfl_sync(FULL, Lij, k);
+      a[k] = fmaf(-Lij, Lkj, a[k]);               // meaningful for rows i >= k
     }
-    d = __shfl_sync(FULL, d, 0);
-    if (lane > j && lane < NL) {
-      float sacc = Lm[lane * NL + j];
-      for (int k = 0; k < j; ++k) sacc -= Lm[lane * NL + k] * Lm[j * NL + k];
-      Lm[lane * NL + j] = sacc * d;
-    }
-    __syncwarp();
   }
+  if (lane < NL) {
+#pragma unroll
+    for (int k = 0; k < NL; ++k) Lm[lane * NL + k] = a[k];   // the strict upper triangle is never read
+  }
+  __syncwarp();
 }
 // per-lane triangular solves  L L^T x = b   (b, x: 9 registers)
 __device__ __forceinline__ void chol9_solve(const float* Lm, const float* b, float* x) {
@@ -456,35 +476,27 @@ __device__ __noinline__ void solve_ik(Smem& s, const float* target, int lane) {
       float r[3] = {s.p[EE][0] - s.p[lane][0], s.p[EE][1] - s.p[lane][1], s.p[EE][2] - s.p[lane][2]};
       cross3(Jc, s.z[lane], r);
     }
-    // A = J^T J + damp I, b = J^T e ; lane i owns row i
-    float Arow[NL];
+    // Damped least squares step  dq = J^T (J J^T + damp I)^-1 e : by the push-through identity this IS the oracle's
+    // (J^T J + damp I)^-1 J^T e, with a 3x3 system instead of a 9x9 one (the form BussIK's CalcDeltaThetasDLS uses).
+    float U[6] = {Jc[0] * Jc[0], Jc[0] * Jc[1], Jc[0] * Jc[2], Jc[1] * Jc[1], Jc[1] * Jc[2], Jc[2] * Jc[2]};
 #pragma unroll
-    for (int j = 0; j < NL; ++j) {
-      float jx = __shfl_sync(FULL, Jc[0], j), jy = __shfl_sync(FULL, Jc[1], j), jz = __shfl_sync(FULL, Jc[2], j);
-      Arow[j] = Jc[0] * jx + Jc[1] * jy + Jc[2] * jz + ((j == lane) ? damp : 0.f);
+    for (int o = 8; o > 0; o >>= 1) {   // lanes 0..15 end up with identical sums (columns live in lanes 0..8)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) U[k] += __shfl_xor_sync(FULL, U[k], o);
     }
-    if (lane < NL) {
-#pragma unroll
-      for (int j = 0; j < NL; ++j) s.dyn.ik.A[lane * NL + j] = Arow[j];
-      s.dyn.ik.b[lane] = Jc[0] * e[0] + Jc[1] * e[1] + Jc[2] * e[2];
-    }
-    __syncwarp();
-    chol9(s.dyn.ik.A, lane);
-    float bb[NL], x[NL];
-#pragma unroll
-    for (int j = 0; j < NL; ++j) bb[j] = s.dyn.ik.b[j];
-    chol9_solve(s.dyn.ik.A, bb, x);  // every lane solves the same system (cheap, avoids a broadcast)
-    float mx = 0.f;
-#pragma unroll
-    for (int j = 0; j < NL; ++j) mx = fmaxf(mx, fabsf(x[j]));
+    // LDL^T of [[a b c] [b d f] [c f g]] + damp I, then two triangular solves
+    const float a_ = U[0] + damp, d0i = 1.f / a_;
+    const float l10 = U[1] * d0i, l20 = U[2] * d0i;
+    const float d1 = U[3] + damp - l10 * U[1], d1i = 1.f / d1;
+    const float t21 = U[4] - l20 * U[1];
+    const float l21 = t21 * d1i;
+    const float d2 = U[5] + damp - l20 * U[2] - l21 * t21, d2i = 1.f / d2;
+    const float y0 = e[0], y1 = e[1] - l10 * y0, y2 = e[2] - l20 * y0 - l21 * y1;
+    const float x2 = y2 * d2i, x1 = y1 * d1i - l21 * x2, x0 = y0 * d0i - l10 * x1 - l20 * x2;
+    const float dq = Jc[0] * x0 + Jc[1] * x1 + Jc[2] * x2;   // zero for lanes that own no column
+    const float mx = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(lane < NL ? fabsf(dq) : 0.f)));
     const float sc = mx > maxang ? maxang / mx : 1.f;
-    __syncwarp();
-    if (lane < NL) {
-      float v = 0.f;
-#pragma unroll
-      for (int j = 0; j < NL; ++j) if (j == lane) v = x[j];
-      s.qik[lane] += sc * v;
-    }
+    if (lane < NL) s.qik[lane] += sc * dq;
     __syncwarp();
   }
 }
@@ -568,22 +580,28 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
     const float* verts = pool + (int)(*(sh + MS_VERT_OFF));
     const float* planes = pool + (int)(*(sh + MS_PLANE_OFF));
     const float smu = (*(sh + MS_MU));
+    // broadphase on the link's bounding sphere: against the table plane and against the block's bounding sphere
+    // (exact: the sphere contains every hull vertex, 1e-4 m of slack covers the fp32 rounding of the transform)
+    float lc[3] = {(*(sh + MS_SPHERE_C)), (*(sh + MS_SPHERE_C + 1)), (*(sh + MS_SPHERE_C + 2))}, cw[3];
+    mat_vec(cw, s.R[l], lc);
+    cw[0] += s.p[l][0]; cw[1] += s.p[l][1]; cw[2] += s.p[l][2];
+    const float srad = (*(sh + MS_SPHERE_R));
+    const bool near_table = cw[2] - srad <= tz + P(s, MP_CONTACT_MARGIN) + 1e-4f;   // uniform
+    float dd[3] = {s.bp[0] - cw[0], s.bp[1] - cw[1], s.bp[2] - cw[2]};
+    const bool near_block = !(sqrtf(dot3(dd, dd)) > srad + brad + block_margin);       // uniform
+    if (!near_table && !near_block) continue;
     float wv[3] = {0, 0, 0};
     if (lane < nv) {
       float lv[3] = {(*(verts + 3 * lane)), (*(verts + 3 * lane + 1)), (*(verts + 3 * lane + 2))};
       mat_vec(wv, s.R[l], lv);
       wv[0] += s.p[l][0]; wv[1] += s.p[l][1]; wv[2] += s.p[l][2];
     }
-    {  // hull vertices vs table plane, up to 2 deepest
+    if (near_table) {  // hull vertices vs table plane, up to 2 deepest
       const float d = wv[2] - tz;
       unsigned m = select_deepest(d, lane < nv, P(s, MP_CONTACT_MARGIN), 2, lane);
       push_contacts(s, m, lane, l, 0, wv, up, d, smu * P(s, MP_MU_TABLE));
     }
-    // broadphase: bounding spheres
-    float lc[3] = {(*(sh + MS_SPHERE_C)), (*(sh + MS_SPHERE_C + 1)), (*(sh + MS_SPHERE_C + 2))}, cw[3];
-    mat_vec(cw, s.R[l], lc);
-    float dd[3] = {s.bp[0] - cw[0] - s.p[l][0], s.bp[1] - cw[1] - s.p[l][1], s.bp[2] - cw[2] - s.p[l][2]};
-    if (sqrtf(dot3(dd, dd)) > (*(sh + MS_SPHERE_R)) + brad + block_margin) continue;  // uniform
+    if (!near_block) continue;
     // candidates: lanes 0..7 = block vertex vs hull planes, lanes 8..8+nv-1 = hull vertex vs block box
     float d = 3.0e38f, nrm[3] = {0, 0, 0}, x[3] = {0, 0, 0};
     bool valid = false;
@@ -648,7 +666,9 @@ __device__ __forceinline__ void plane_space(const float* n, float* p, float* q) 
 __device__ __noinline__ void substep_dynamics(Smem& s, const EnvParams& ep, const float* __restrict__ model_g, int lane) {
   const float dt = P(s, MP_DT), gz = P(s, MP_GRAVITY), kl = P(s, MP_LIN_DAMP), ka = P(s, MP_ANG_DAMP);
   fk(s, s.q, lane);
+  PROF_T0();
   joint_space_dynamics(s, gz, kl, ka, lane);
+  PROF_ADD(s.prof_e, 2);
   chol9(s.dyn.L, lane);
   // M^-1 columns (lanes 0..8) and unconstrained acceleration (lane 9)
   if (lane <= NL) {
@@ -676,7 +696,9 @@ __device__ __noinline__ void substep_dynamics(Smem& s, const EnvParams& ep, cons
     const float wn = sqrtf(dot3(s.bw, s.bw));
     s.u[lane] = s.bw[a] + dt * (-(ka + ka * wn) * s.bw[a]);
   } else if (lane == 15) s.u[15] = 0.f;
+  PROF_ADD(s.prof_e, 3);
   find_contacts(s, ep, model_g, P(s, MP_BLOCK_MARGIN), lane);
+  PROF_ADD(s.prof_e, 4);
   if (lane < 9) {  // world-frame inverse inertia of the block: R diag(1/I) R^T
     const int r = lane / 3, cc = lane % 3;
     s.Ibinv[lane] = s.Rb[3 * r] * s.Rb[3 * cc] / ep.binertia[0] + s.Rb[3 * r + 1] * s.Rb[3 * cc + 1] / ep.binertia[1] +
@@ -701,17 +723,6 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
   return y;
 }
 
-#ifdef BMI_PROF
-// Debug build only (tools/prof_rollout_phases.py): per-env cycle counters of the fused rollout.
-__device__ unsigned long long g_prof[8192 * 8];
-#define PROF_T0() long long prof_t0 = clock64()
-#define PROF_ADD(e, k) do { const long long t1_ = clock64(); if (lane == 0 && (e) < 8192) g_prof[(e) * 8 + (k)] += (unsigned long long)(t1_ - prof_t0); prof_t0 = t1_; } while (0)
-#define PROF_CNT(e, k, v) do { if (lane == 0 && (e) < 8192) g_prof[(e) * 8 + (k)] += (unsigned long long)(v); } while (0)
-#else
-#define PROF_T0()
-#define PROF_ADD(e, k)
-#define PROF_CNT(e, k, v)
-#endif
 
 // ---- constraint rows + projected Gauss-Seidel + integration ------------------------------------------------------
 // Same rows, row order, clamps and residual exit as pgs_solve in oracle/bmi_physics_oracle.c (Bullet's order: motors,
@@ -727,6 +738,7 @@ __device__ unsigned long long g_prof[8192 * 8];
 // (contact row -> contact row), precomputed once per sub-step into s.Minv / s.S.  In exact arithmetic the iterates are
 // those of the velocity-space solver.
 __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lane) {
+  PROF_T0();
   const float dt = P(s, MP_DT);
   const int nc = s.nc, nrows = 3 * nc;
   const bool has_arm = s.na > 0;        // uniform
@@ -862,6 +874,7 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   const int max_it = (int)P(s, MP_SOLVER_ITERS);
   const float thresh = P(s, MP_RESIDUAL_THRESH);
   int it = 0;
+  PROF_ADD(s.prof_e, 5);
   // one joint-source update: every lane adds its coefficient x d (contact lanes: all three rows, only when some
   // contact touches the arm — otherwise their coefficients are zero)
 #define BMI_JOINT_EVENT(ARM, joff, dj)                                                    \
@@ -939,9 +952,7 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   }
 #undef BMI_JOINT_ROWS
 #undef BMI_JOINT_EVENT
-#ifdef BMI_PROF
-  if (lane == 0) s.prof_iters = it;
-#endif
+  PROF_CNT(s.prof_e, 7, it);
   // ---- integrate --------------------------------------------------------------------------------------------------
   const float unew = lane < NU ? s.u[lane] + v0 : 0.f;
   if (lane < NL) {
@@ -971,6 +982,7 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
     s.bq[0] = r[0] * inv; s.bq[1] = r[1] * inv; s.bq[2] = r[2] * inv; s.bq[3] = r[3] * inv;
   }
   __syncwarp();
+  PROF_ADD(s.prof_e, 6);
 }
 
 
@@ -1100,19 +1112,17 @@ __device__ __noinline__ void env_step_begin(Smem& s, const EnvParams& ep, const 
 __device__ __forceinline__ void env_step_warp(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
                                               const float* a_in, int lane, int e) {
   PROF_T0();
+#ifdef BMI_PROF
+  if (lane == 0) s.prof_e = e;
+  __syncwarp();
+#endif
   env_step_begin(s, ep, model_g, a_in, lane);
   PROF_ADD(e, 1);
   const int nsub = (int)P(s, MP_N_SUBSTEPS);
   for (int i = 0; i < nsub; ++i) {
     substep_dynamics(s, ep, model_g, lane);
-    PROF_ADD(e, 2);
     substep_solve(s, ep, lane);
-    PROF_ADD(e, 3);
-#ifdef BMI_PROF
-    PROF_CNT(e, 5, s.prof_iters);
-    PROF_CNT(e, 6, s.prof_iters >= 150 ? 1 : 0);
-    PROF_CNT(e, 7, s.nc);
-#endif
+    PROF_RESET();
   }
 }
 

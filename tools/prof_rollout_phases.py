@@ -8,7 +8,7 @@ import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rl_arm_under_sparse_reward_b200 import _build
-lib_path = os.path.join(_build.OUT_DIR, "libbmi_b200_prof.so")
+lib_path = os.environ.get("BMI_PROF_LIB", os.path.join(_build.OUT_DIR, "libbmi_b200_prof.so"))
 if "--no-build" not in sys.argv:
     _build.build(force=True, verbose=False, extra_flags=["-DBMI_PROF"], lib_path=lib_path, obj_suffix="_prof")
 os.environ["BMI_B200_LIB"] = lib_path
@@ -36,18 +36,18 @@ for rep in range(2):
     out = np.zeros((8192, 8), dtype=np.uint64)
     dbg(out.ctypes.data_as(ctypes.c_void_p), out.size, 0)
     out = out[:n].astype(np.float64)
-    names = ["policy", "ik+begin", "pre", "solve+integrate", "(unused)", "iters", "substeps@150", "contacts"]
-    tot = out[:, :5].sum(1)
+    names = ["policy", "ik+begin", "fk+dynamics", "chol+Minv+u", "contacts", "rows+Delassus", "PGS loop+integrate", "iters"]
+    tot = out[:, :7].sum(1)
     print("rollout %d: %.1f ms (%.0f env-steps/s); per-env busy cycles: median %.3g max %.3g (=%.1f ms at 1.965 GHz)" % (
         rep, ms, n * T / ms * 1e3, np.median(tot), tot.max(), tot.max() / 1.965e6))
     nsub = T * 20
     for k, nm in enumerate(names):
         c = out[:, k]
-        unit = "cycles/substep" if k < 5 else "per substep"
-        print("  %-13s mean %10.1f  median %10.1f  p90 %10.1f  max %10.1f  %s" % (
+        unit = "cycles/substep" if k < 7 else "per substep"
+        print("  %-18s mean %10.1f  median %10.1f  p90 %10.1f  max %10.1f  %s" % (
             nm, c.mean() / nsub, np.median(c) / nsub, np.percentile(c, 90) / nsub, c.max() / nsub, unit))
-    slow = np.argsort(-tot)[:5]
+    slow = np.argsort(-tot)[:3]
     for e_ in slow:
         print("  slow env %5d: total %.3g  " % (e_, tot[e_]) + " ".join("%s=%.0f" % (nm, out[e_, k] / nsub) for k, nm in enumerate(names)))
-    wait_per_it = out[:, 3] / np.maximum(out[:, 5], 1)
-    print("  solve cycles per iteration: median %.0f  p90 %.0f  max %.0f" % (np.median(wait_per_it), np.percentile(wait_per_it, 90), wait_per_it.max()))
+    per_it = out[:, 6] / np.maximum(out[:, 7], 1)
+    print("  PGS cycles per iteration: median %.0f  p90 %.0f  max %.0f" % (np.median(per_it), np.percentile(per_it, 90), per_it.max()))
