@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 N_ENVS = 4096
 T = 100
 ALGO_BYTES_PER_ENV_STEP = 412          # state in+out 2x136 + action 16 + episode write 124
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_kernel launch (4096 envs x 100 steps), from the
+# `ncu --set full` capture summarised in profiles/r01_rollout_kernel_ncu.md (bench.py cannot run ncu itself)
+NCU_DRAM_BYTES_PER_LAUNCH = 80482304   # 4.774 MB read + 75.708 MB written
 METRIC = "env-steps/s (push, 4096 envs) at 1/2/4/8 B200 vs CPU PyBullet+MPI"
 
 
@@ -175,8 +178,16 @@ def run_gpu(args):
     agent = ddpg_agent(a, env, get_env_params(env))
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
-    def cycle():
+    roll_ev = []
+
+    def cycle(timed=False):
+        if timed:   # CUDA events around the rollout launch of THIS cycle (on the launching stream)
+            rs, re_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rs.record()
         agent.rollout(0)
+        if timed:
+            re_.record()
+            roll_ev.append((rs, re_))
         agent.buffer.store_episode([agent.ep['obs'], agent.ep['ag'], agent.ep['g'], agent.ep['actions']])
         agent._update_normalizer()
         agent.update_many(a.n_batches)
@@ -205,7 +216,7 @@ def run_gpu(args):
     for s, e in ev:
         flush.fill_(1.0)               # L2 flush between timed iterations (outside the timed event pair)
         s.record()
-        cycle()
+        cycle(timed=True)
         e.record()
     barrier()
     ms = np.array([s.elapsed_time(e) for s, e in ev])
@@ -216,18 +227,10 @@ def run_gpu(args):
     env_steps_per_cycle = a.n_envs * T
     value = world * env_steps_per_cycle * args.steps / (total_ms * 1e-3)
 
-    # ---- instrumented pass: CUDA events around the rollout launch of the same K cycles ----------------------------
+    # ---- dominant kernel: CUDA events recorded around the rollout launch inside each of the K timed cycles -------------
     # (the fused rollout kernel is ONE launch per batch of episodes: T env-steps for each of the n_envs envs; the
-    # events also bracket the four tiny weight-transpose launches and the placement draw, < 0.1 % of the interval)
-    t_roll = []
-    for _ in range(args.steps):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        agent.rollout(0)
-        e.record()
-        t_roll.append((s, e))
-    torch.cuda.synchronize()
-    kern_ms = float(np.mean([s.elapsed_time(e) for s, e in t_roll]))
+    # events also bracket the four tiny weight-transpose launches, < 0.1 % of the interval)
+    kern_ms = float(np.mean([s.elapsed_time(e) for s, e in roll_ev]))
     kernel_name = "rollout_kernel" if getattr(a, "fused_rollout", True) else "env_step_kernel x %d" % T
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_ENV_STEP * a.n_envs * T / (kern_ms * 1e-3) / 1e9
@@ -309,7 +312,7 @@ def run_gpu(args):
                            "envs_per_gpu": a.n_envs, "updates_per_env_step": a.n_batches / env_steps_per_cycle,
                            "buffer_episodes": args.buffer_episodes, "l2": "flushed between timed iterations (256 MiB fill)",
                            "parallelism": "dp%d" % world},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                              "kernel": kernel_name, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * a.n_envs * T,
                              "kernel_ms": kern_ms, "kernel_share_of_step": kernel_share, "peak_source": peak_src,
                              "note": "FP32-issue/latency-bound kernel: the HBM fraction is small by construction (SURVEY 8d)"},
