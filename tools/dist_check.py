@@ -10,7 +10,9 @@ from rl_arm_under_sparse_reward_b200 import utils
 
 
 def log(*a):
-    print("[rank %s %.1fs]" % (os.environ.get("RANK"), time.time() - T0), *a, flush=True)
+    # ONE write per line: two ranks share the pipe and print() emits its arguments piecewise
+    sys.stdout.write("[rank %s %.1fs] %s\n" % (os.environ.get("RANK"), time.time() - T0, " ".join(str(x) for x in a)))
+    sys.stdout.flush()
 
 
 T0 = time.time()
