@@ -30,7 +30,7 @@ flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 ctr = torch.zeros(1, dtype=torch.int64, device=dev)
 nv = torch.tensor([E], dtype=torch.int64, device=dev)
 rows = []
-for B in (256, 1024, 4096, 16384, 65536):
+for B in (256, 1024, 4096, 16384, 65536, 262144, 1048576):
     d = (torch.empty(B, dtype=torch.int64, device=dev), torch.empty(B, dtype=torch.int64, device=dev),
          torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.float64, device=dev))
     X, XN, A, R = (torch.empty(B, 30, device=dev), torch.empty(B, 30, device=dev), torch.empty(B, 4, device=dev), torch.empty(B, device=dev))
