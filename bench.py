@@ -264,16 +264,18 @@ def run_gpu(args):
                 rs_host[1].copy_(s, non_blocking=True)
                 h2d += act_dev.numel() * 4
                 d2h += (obs.numel() + ag.numel() + r.numel() + s.numel()) * 4
+            # The host now holds the cycle's time-major record (what a host-driven loop accumulates step by step).
+            # Episode batch for store_episode / _update_normalizer: ONE pinned H2D copy per array, transposed to the
+            # reference's (R, T+1, dim) layout on the device (a 60 MB strided transpose on the host costs more than
+            # the whole update phase).
             torch.cuda.synchronize()
-            # episode batch in the reference's (R, T+1, dim) host layout -> store_episode (H2D inside)
-            mb_obs = obs_host.permute(1, 0, 2).contiguous()
-            mb_ag = ag_host.permute(1, 0, 2).contiguous()
-            mb_g = g_host[:, None, :].expand(a.n_envs, T, 3).contiguous()
-            mb_act = act_host.permute(1, 0, 2).contiguous()
+            mb_obs = obs_host.to(dev, non_blocking=True).permute(1, 0, 2).contiguous()
+            mb_ag = ag_host.to(dev, non_blocking=True).permute(1, 0, 2).contiguous()
+            mb_g = g_host.to(dev)[:, None, :].expand(a.n_envs, T, 3).contiguous()
+            mb_act = act_host.to(dev, non_blocking=True).permute(1, 0, 2).contiguous()
+            h2d += (obs_host.numel() + ag_host.numel() + g_host.numel() + act_host.numel()) * 4
             agent.buffer.store_episode([mb_obs, mb_ag, mb_g, mb_act])
-            h2d += (mb_obs.numel() + mb_ag.numel() + mb_g.numel() + mb_act.numel()) * 4
-            agent._update_normalizer([mb_obs.to(dev), mb_ag.to(dev), mb_g.to(dev), mb_act.to(dev)])
-            h2d += (mb_obs.numel() + mb_ag.numel() + mb_g.numel() + mb_act.numel()) * 4
+            agent._update_normalizer([mb_obs, mb_ag, mb_g, mb_act])
             agent.update_many(a.n_batches)
             agent._soft_update_target_network()
             loss_host.copy_(agent._losses, non_blocking=True)
@@ -292,7 +294,7 @@ def run_gpu(args):
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
         e2e = {"value": world * env_steps_per_cycle * n_e2e / float(el.item()), "unit": "env-steps/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "note": "host (pinned) action/obs buffers every env-step, host episode batch into store_episode, loss read back"}
+               "note": "host (pinned) action/obs buffers every env-step through env.step, the host-side episode record uploaded (pinned H2D) into store_episode / _update_normalizer, loss read back"}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

@@ -240,7 +240,7 @@ int bmi_select_actions(const float* pi_dev, int64_t n, int32_t act_dim, float ac
 
 /* ------------------------------------------------------------------------------------
  * Vectorised bmirobot environment (bmirobot_env_push_F.py:92-245, bmirobot.py:129-191,
- * bmirobot_inverse_kinematics.py:28-33).  One CUDA thread block per env instance.
+ * bmirobot_inverse_kinematics.py:28-33).  One warp per env instance, 28 envs per thread block.
  * ---------------------------------------------------------------------------------- */
 typedef struct bmi_env bmi_env;
 #define BMI_TASK_PUSH 0

@@ -1,7 +1,8 @@
-// Vectorised bmirobot environment: one CUDA thread block (one warp) per env instance.
+// Vectorised bmirobot environment: one WARP per env instance, 28 envs per thread block, one block per SM
+// (4096 envs = 147 blocks = one resident wave on a B200).
 //
 // Reference behaviour restated (paths relative to the reference tree; the arithmetic itself
-// lives in PyBullet, so the algorithm follows oracle/bmi_physics_oracle.c line for line):
+// lives in PyBullet, so the algorithm follows oracle/bmi_physics_oracle.c):
 //   bmirobot_env/bmirobot_env_push_F.py:92-108   step: clip, action[3]=0, IK + motors, 20 sub-steps
 //   bmirobot_env/bmirobot_env_push_F.py:110-165  reset (block / goal placement ranges)
 //   bmirobot_env/bmirobot_env_push_F.py:169-237  27-float observation
@@ -9,14 +10,15 @@
 //   bmirobot_env/bmirobot_inverse_kinematics.py:28-33  position-only DLS IK of link 11
 //   bmirobot_env/bmirobot_env_pickandplace_v2.py:92-95,116-131  pick task deltas
 //
-// Per sub-step: forward kinematics -> mass matrix + bias by 10 lane-parallel recursive
-// Newton-Euler sweeps (lane j < 9: unit acceleration e_j, lane 9: velocity/gravity/damping bias)
-// -> Cholesky -> unconstrained velocities -> contact generation (lane = vertex) -> constraint
-// rows (lane = row) -> projected Gauss-Seidel with warp-shuffle dot products (lane = generalized
-// velocity) -> semi-implicit Euler.  fp32 throughout, no tensor cores.
-// The kinematic tree + solver constants (header + 9 link records of the model blob, 1408 B) are
-// staged into shared memory by one TMA bulk copy per block; convex-polytope vertex/plane pools
-// are read through the read-only path (they are shared by every block and stay in L1/L2).
+// Per sub-step: forward kinematics -> mass matrix by composite rigid bodies + bias by one
+// Newton-Euler pass (joint_space_dynamics) -> register-resident Cholesky -> M^-1 -> unconstrained
+// velocities -> contact generation (lane = vertex, bounding-sphere broadphase) -> constraint rows
+// (lane = row) and their coupling table -> projected Gauss-Seidel in constraint space (lane = joint /
+// block velocity component / contact; one shuffle per row update, substep_solve) -> semi-implicit
+// Euler.  fp32 throughout, no tensor cores.
+// The WHOLE model blob (solver constants, joint tree, collision polytopes: 5.5 KB) is staged into
+// shared memory by one TMA bulk copy per block: the env working sets fill the SM's shared memory, so
+// there is no L1 left and anything read from global memory would be an L2 round trip.
 #include "common.cuh"
 #include "../../include/bmi_model.h"
 

@@ -80,3 +80,22 @@ def test_env_placement_draw_order_matches_reference_semantics():
                 break
         assert random.getstate() == state_after
         assert np.allclose(p[:3], [x, y, 0.2]) and np.allclose(p[4:7], [xt, yt, zt])
+
+
+def test_kernel_and_oracle_share_contact_caps_and_model_constants():
+    """The CUDA env kernel and the C oracle must agree on the contact caps (they change the physics when they bind)
+    and on the model-blob layout they both parse."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cu = open(os.path.join(root, "rl_arm_under_sparse_reward_b200", "csrc", "physics.cu")).read()
+    oc = open(os.path.join(root, "oracle", "bmi_physics_oracle.c")).read()
+    maxc = int(re.search(r"constexpr int MAXC = (\d+);", cu).group(1))
+    maxa = int(re.search(r"constexpr int MAXA = (\d+);", cu).group(1))
+    assert maxc == int(re.search(r"#define MAX_CONTACTS (\d+)", oc).group(1))
+    assert maxa == int(re.search(r"#define MAX_ARM_CONTACTS (\d+)", oc).group(1))
+    # one solver lane per contact next to 9 joint lanes and 6 block-velocity lanes
+    assert 16 + maxc <= 32 and 3 * maxc <= 32
+    blob = np.fromfile(os.path.join(root, "rl_arm_under_sparse_reward_b200", "assets", "bmirobot_model.bin"), "<f4")
+    staged = int(re.search(r"constexpr int STAGED_FULL = (\d+);", cu).group(1))
+    assert blob.shape[0] == int(blob[7]) <= staged          # MP_TOTAL; the env kernels stage the whole blob
+    assert int(blob[2]) == 9 and int(blob[3]) <= 4           # links, shapes

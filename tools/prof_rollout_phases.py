@@ -1,8 +1,10 @@
 """Where does a fused rollout's time go, per env?  Builds an instrumented copy of the library (-DBMI_PROF: clock64
-counters around policy / IK / sub-step set-up / solver wait / integrate, plus solver iteration counts) and prints the
-distribution over envs.  Debug tool: the numbers are cycles of the env's own warp, not a benchmark.
+counters around policy / IK / fk+dynamics / Cholesky+M^-1 / contacts / rows+Delassus table / PGS loop+integrate, plus
+solver iteration counts) and prints the distribution over envs.  Debug tool: the numbers are cycles of the env's own
+warp, not a benchmark.
 
-    python tools/prof_rollout_phases.py [n_envs] [T]
+    python tools/prof_rollout_phases.py [n_envs] [T] [--no-build]
+    BMI_PROF_LIB=<lib built with -DBMI_PROF -DBMI_ENVS_PER_BLOCK=1> ... 148 100 --no-build    (one env per SM: lone-warp latencies)
 """
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
