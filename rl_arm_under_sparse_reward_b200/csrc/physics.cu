@@ -19,6 +19,8 @@
 // The WHOLE model blob (solver constants, joint tree, collision polytopes: 5.5 KB) is staged into
 // shared memory by one TMA bulk copy per block: the env working sets fill the SM's shared memory, so
 // there is no L1 left and anything read from global memory would be an L2 round trip.
+#include <vector>
+
 #include "common.cuh"
 #include "../../include/bmi_model.h"
 
@@ -30,7 +32,13 @@ constexpr int EE = 8;          // right_hand2
 constexpr int MAXC = 9;        // contacts per sub-step (one solver lane each)
 constexpr int MAXA = 6;        // ... of which at most 6 involve an arm link
 constexpr int MAXR = 3 * MAXC; // contact rows: normal + two friction directions per contact
-constexpr int STAGED = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;  // floats staged by TMA (reset kernel: joint tree only)
+// The device copy of the model keeps the link records at a stride of 33 floats (the file format's 32 would put the same
+// field of all nine links into ONE shared-memory bank: every "lane = link" read was a 9-way conflict); bmi_env_create
+// re-strides the blob and shifts the shape / pool offsets by LINK_SHIFT.
+constexpr int LINK_STRIDE_DEV = BMI_LINK_STRIDE + 1;
+constexpr int LINK_REGION_DEV = ((BMI_MAX_LINKS * LINK_STRIDE_DEV + 3) / 4) * 4;          // 300 floats (keeps 16-byte alignment)
+constexpr int LINK_SHIFT = LINK_REGION_DEV - BMI_MAX_LINKS * BMI_LINK_STRIDE;             // 12
+constexpr int STAGED = BMI_MODEL_HDR + LINK_REGION_DEV;  // floats staged by TMA (reset kernel: joint tree only)
 constexpr int STAGED_FULL = 1408;  // env kernels stage the WHOLE blob (joint tree + collision polytopes); capacity in floats
 constexpr int HID = 256;         // hidden width of the actor (models.py:15-17)
 constexpr unsigned FULL = 0xffffffffu;
@@ -68,7 +76,8 @@ static_assert(ENVW >= 1 && ENVW <= 32, "one warp per env, at most 1024 threads p
 // LANE_CT + c owns contact c (its normal and two friction rows).
 constexpr int LANE_BLK = 9, LANE_CT = 16;
 static_assert(LANE_CT + MAXC <= 32 && MAXR <= 32, "one lane per contact, one lane per contact row in the set-up");
-constexpr int MS = 13;            // row stride of M^-1 (odd: lanes i = 0..8 reading entry (i, j) hit distinct banks)
+constexpr int MS = 11;            // row stride of M^-1: lanes i = 0..8 reading entry (i, j) hit banks 11 i + j = {0,11,22,1,12,23,2,13,24} + j,
+                                  // which leaves the runs 3..10 and 14..21 free for the contact lanes / the zero row (see Smem)
 constexpr int SCOL_BLK = 9;       // coupling-table columns: [0, 9) joints, [9, 15) block velocity, [15, 15 + MAXR) contact rows
 constexpr int SCOL_CT = 15;
 constexpr int SS = SCOL_CT + MAXR + ((SCOL_CT + MAXR) % 2 == 0 ? 1 : 0);  // odd row stride
@@ -78,7 +87,6 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
   const float* model;             // block-shared header params + link records (the TMA destination)
   int nc, na;                     // contacts, contacts on arm links
   float R[NL][9], p[NL][3], z[NL][3], c[NL][3];
-  float Minv[NL * MS];            // M^-1 (symmetric), entry (i, j) at [i * MS + j]
   float q[NL], qd[NL], qt[NL], bias[NL], acc[NL];
   float u[16];
   float bp[3], bq[4], bv[3], bw[3], goal[3];
@@ -88,8 +96,14 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
   int clink[MAXC], chasb[MAXC], carm[MAXC];   // carm: arm slot of a contact or -1
   // Coupling table of the constraint solver.  Row x (one per contact row, x = 3 c + k) holds what a unit impulse on
   // that row does to every solver variable: [0, 9) the joint velocities (M^-1 Ja^T), [9, 15) the block velocity,
-  // [15 + y] the constraint-space velocity of contact row y (the Delassus entry J_y M^-1 J_x^T).  Row MAXR is zero.
-  float S[(MAXR + 1) * SS];
+  // [15 + y] the constraint-space velocity of contact row y (the Delassus entry J_y M^-1 J_x^T).
+  // Minv, S and zero9 are laid out back to back on purpose: in one solver load the joint lanes read Minv (banks
+  // 11 i + j), contact lane c reads S row 3 c (bank 3 + c + j relative to Minv, since 99 = 3 and 3 * 43 = 1 mod 32) and
+  // the block / idle lanes read zero9 (bank 16 + j): no two of them share a bank for up to 8 contacts.
+  float Minv[NL * MS];            // M^-1 (symmetric), entry (i, j) at [i * MS + j]
+  float S[MAXR * SS];
+  float zpad[4];
+  float zero9[12];                // coefficients of the lanes a joint row does not touch
   union {
     struct {
       union {
@@ -121,7 +135,7 @@ struct EnvParams {
 };
 
 __device__ __forceinline__ float P(const Smem& s, int i) { return s.model[i]; }
-__device__ __forceinline__ const float* LK(const Smem& s, int i) { return s.model + BMI_MODEL_HDR + i * BMI_LINK_STRIDE; }
+__device__ __forceinline__ const float* LK(const Smem& s, int i) { return s.model + BMI_MODEL_HDR + i * LINK_STRIDE_DEV; }
 
 __device__ __forceinline__ float& MINV(Smem& s, int i, int j) { return s.Minv[i * MS + j]; }
 
@@ -828,7 +842,7 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
     }
     s.rows.sc[lane] = make_float4(invd, rhs, diag, s.cmu[ci]);
   }
-  if (lane < SS) s.S[MAXR * SS + lane] = 0.f;   // the zero row
+  if (lane < 12) s.zero9[lane] = 0.f;
   __syncwarp();
   // ---- Delassus entries: lane y fills column SCOL_CT + y of every row x:  J_y . (M^-1 J_x^T) ------------------------
   {
@@ -858,7 +872,7 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   // Only contact lanes own three variables; for the others k = 1, 2 read in-bounds don't-care words into v1 / v2,
   // which they never use (that keeps ONE address register per event type and immediate offsets for k).
   const unsigned s_base = (unsigned)__cvta_generic_to_shared(s.S);
-  unsigned ja = s_base + MAXR * SS * 4u, ca = s_base;   // default: the zero row / column 0 (idle lanes)
+  unsigned ja = (unsigned)__cvta_generic_to_shared(s.zero9), ca = s_base;   // default: the zero row / column 0 (idle lanes)
   const int myc = lane - LANE_CT;
   if (lane < NL) {
     ja = (unsigned)__cvta_generic_to_shared(s.Minv) + (unsigned)lane * (MS * 4u);
@@ -1071,6 +1085,8 @@ struct BlockSmem {
   Smem sw[ENVW];
 };
 static_assert(sizeof(Smem) % 16 == 0, "Smem slots must be 16-byte aligned");
+static_assert((offsetof(Smem, S) - offsetof(Smem, Minv)) / 4 % 32 == 3 && (offsetof(Smem, zero9) - offsetof(Smem, Minv)) / 4 % 32 == 16,
+              "bank layout of the solver tables (see Smem)");
 static_assert(offsetof(BlockSmem, sw) % 16 == 0, "Smem slots must be 16-byte aligned");
 static_assert((sizeof(BlockSmem) + 1024) * BLOCKS_PER_SM <= 228 * 1024, "BLOCKS_PER_SM blocks (+1 KB reserved each) must fit the SM's 228 KB");
 template <int N> struct PrintSize;
@@ -1408,8 +1424,9 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   const int64_t n = bytes / 4;
   BMI_REQUIRE(b[MP_MAGIC] == BMI_MODEL_MAGIC && (int64_t)b[MP_TOTAL] == n && n <= BMI_MODEL_MAX_FLOATS,
               "bmi_env_create: model blob magic/size mismatch");
-  BMI_REQUIRE(n <= STAGED_FULL, "bmi_env_create: model blob (%lld floats) exceeds the shared-memory staging area (%d)",
-              (long long)n, STAGED_FULL);
+  BMI_REQUIRE(n + LINK_SHIFT <= STAGED_FULL, "bmi_env_create: model blob (%lld floats) exceeds the shared-memory staging area (%d)",
+              (long long)n, STAGED_FULL - LINK_SHIFT);
+  BMI_REQUIRE((int)b[MP_SHAPES_OFF] >= BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE, "bmi_env_create: shapes overlap the link records");
   BMI_REQUIRE((int)b[MP_N_LINKS] == NL && (int)b[MP_EE_LINK] == EE && (int)b[MP_N_SHAPES] <= BMI_MAX_SHAPES &&
                   (int)b[MP_LINKS_OFF] == BMI_MODEL_HDR,
               "bmi_env_create: model does not match the compiled arm topology");
@@ -1439,16 +1456,26 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   h->ep.binertia[0] = mm * (ly * ly + lz * lz);
   h->ep.binertia[1] = mm * (lx * lx + lz * lz);
   h->ep.binertia[2] = mm * (lx * lx + ly * ly);
-  h->model_floats = n;
-  h->model_bytes = (unsigned)(((n * sizeof(float) + 15) / 16) * 16);
+  // device copy with the link records re-strided (LINK_STRIDE_DEV) and everything behind them shifted by LINK_SHIFT
+  const int64_t nd = n + LINK_SHIFT;
+  std::vector<float> dev((size_t)((nd + 3) / 4) * 4, 0.f);
+  for (int i = 0; i < BMI_MODEL_HDR; ++i) dev[i] = b[i];
+  for (int i = 0; i < NL; ++i)
+    for (int k = 0; k < BMI_LINK_STRIDE; ++k) dev[BMI_MODEL_HDR + i * LINK_STRIDE_DEV + k] = b[BMI_MODEL_HDR + i * BMI_LINK_STRIDE + k];
+  const int tail0 = BMI_MODEL_HDR + BMI_MAX_LINKS * BMI_LINK_STRIDE;
+  for (int64_t i = tail0; i < n; ++i) dev[i + LINK_SHIFT] = b[i];
+  dev[MP_SHAPES_OFF] += (float)LINK_SHIFT;
+  dev[MP_POOL_OFF] += (float)LINK_SHIFT;
+  dev[MP_TOTAL] = (float)nd;
+  h->model_floats = nd;
+  h->model_bytes = (unsigned)(dev.size() * sizeof(float));
   if (cudaMalloc(&h->model_dev, h->model_bytes) != cudaSuccess ||
       cudaMalloc(&h->state_dev, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)) != cudaSuccess) {
     set_error("bmi_env_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     bmi_env_destroy(h);
     return BMI_ERR_CUDA;
   }
-  BMI_CUDA_CHECK(cudaMemset(h->model_dev, 0, h->model_bytes));
-  BMI_CUDA_CHECK(cudaMemcpy(h->model_dev, blob, n * sizeof(float), cudaMemcpyHostToDevice));
+  BMI_CUDA_CHECK(cudaMemcpy(h->model_dev, dev.data(), h->model_bytes, cudaMemcpyHostToDevice));
   BMI_CUDA_CHECK(cudaMemset(h->state_dev, 0, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)));
   *out = h;
   return BMI_OK;
