@@ -313,7 +313,10 @@ def run_gpu(args):
                                        "(future k=4) DDPG updates of batch %d + Polyak" % (a.n_envs, env_steps_per_cycle, a.n_batches, a.batch_size),
                            "envs_per_gpu": a.n_envs, "updates_per_env_step": a.n_batches / env_steps_per_cycle,
                            "buffer_episodes": args.buffer_episodes, "l2": "flushed between timed iterations (256 MiB fill)",
-                           "parallelism": "dp%d" % world},
+                           "parallelism": "dp%d" % world,
+                           "grad_sync": ("none (1 rank)" if world == 1 else ("fused peer-memory sum + Adam kernel (CUDA IPC over NVLink)"
+                                         if agent._p2p else "NCCL allreduce (sum) + Adam")),
+                           "p2p_timed_out": bool(agent.p2p_timed_out()) if (world > 1 and agent._p2p) else False},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                              "kernel": kernel_name, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * a.n_envs * T,
                              "kernel_ms": kern_ms, "kernel_share_of_step": kernel_share, "peak_source": peak_src,
