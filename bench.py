@@ -203,7 +203,8 @@ def run_gpu(args):
         cycle()
     barrier()
     sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
+    if rank == 0:          # one nvidia-smi poller per job is enough (rank 0 prints the line)
+        sampler.start()
     # launches per cycle: graph replays do not pass through the host launch counter, so count one eager cycle
     a.use_cuda_graphs = False
     n0 = _lib.launch_count()
@@ -296,7 +297,8 @@ def run_gpu(args):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
                "note": "host (pinned) action/obs buffers every env-step through env.step, the host-side episode record uploaded (pinned H2D) into store_episode / _update_normalizer, loss read back"}
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
