@@ -322,7 +322,7 @@ def run_gpu(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                              "kernel": kernel_name, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * a.n_envs * T,
                              "kernel_ms": kern_ms, "kernel_share_of_step": kernel_share, "peak_source": peak_src,
-                             "note": "FP32-issue/latency-bound kernel: the HBM fraction is small by construction (SURVEY 8d)"},
+                             "note": "FP32-issue/latency-bound kernel, the HBM fraction is small by construction (SURVEY 8d); ncu (profiles/r01_rollout_kernel_ncu.md): 22.9 k warp instructions per env sub-step, issue slots busy 63-68 % of active cycles, the launch ends with its slowest env (median env: half the launch)"},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps),
                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
