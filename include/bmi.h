@@ -288,6 +288,13 @@ typedef struct bmi_rollout_args {
   float* obs; float* ag; float* g; float* success;   /* device outputs after the last step (may be NULL) */
 } bmi_rollout_args;
 int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* args, bmi_stream_t stream);
+/* EXPERIMENTAL (round 1: written, validated against bmi_env_rollout only at the end of the round — see DESIGN.md 8):
+ * the same rollout, bit for bit, with env-steps handed out from a task queue instead of one warp per env for the whole
+ * episode.  Blocks [0, express_blocks) run only express_warps warps each and take the envs whose last step needed the
+ * most solver iterations; all other warps take the cheapest env that is furthest behind.  express_blocks = 0 gives a
+ * plain work queue. */
+int bmi_env_rollout_queue(bmi_env* h, const bmi_rollout_args* args, int32_t express_blocks, int32_t express_warps,
+                          bmi_stream_t stream);
 /* torch-layout flat actor parameters (W[out][in], b per layer) -> W^T[in][out], b per layer */
 int bmi_actor_transpose(const float* actor_params_dev, int32_t obs_dim, int32_t goal_dim, int32_t act_dim,
                         int32_t hidden, float* actor_t_dev, bmi_stream_t stream);

@@ -100,6 +100,7 @@ SIGNATURES = {
     "bmi_env_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     "bmi_env_rollout": (c_int32, [c_void_p, POINTER(RolloutArgs), c_void_p]),
+    "bmi_env_rollout_queue": (c_int32, [c_void_p, POINTER(RolloutArgs), c_int32, c_int32, c_void_p]),
     "bmi_actor_transpose": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "bmi_env_get_state": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "bmi_env_set_state": (c_int32, [c_void_p, c_void_p, c_void_p]),

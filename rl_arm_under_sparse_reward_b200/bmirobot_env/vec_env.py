@@ -73,10 +73,12 @@ class BmiVecEnv:
         return self.obs, self.ag, self.reward, self.success
 
     def rollout(self, T, actor_t, o_norm, g_norm, clip_range, explore, noise_eps=0.0, random_eps=0.0, late_clip=0.0,
-                seed=0, counter=None, episodes=None, reset=True):
+                seed=0, counter=None, episodes=None, reset=True, queue=None):
         """Fused rollout: ONE kernel launch runs T policy + env steps for every env (bmi_env_rollout).
         actor_t: transposed flat actor parameters (bmi_actor_transpose); o_norm/g_norm: normalizer objects;
-        episodes: dict of float32 staging tensors obs/ag/g/actions or None.  Returns (obs, ag, g, success)."""
+        episodes: dict of float32 staging tensors obs/ag/g/actions or None.  Returns (obs, ag, g, success).
+        queue=(express_blocks, express_warps) runs the EXPERIMENTAL task-queue kernel (bmi_env_rollout_queue: same
+        episodes bit for bit, env-steps scheduled dynamically) instead."""
         if reset:
             _lib.call("bmi_env_sample_init", self._h, ctypes.c_uint64(self.seed_value), _lib.ptr(self.counter),
                       _lib.ptr(self.init), _lib.stream_ptr())
@@ -89,7 +91,10 @@ class BmiVecEnv:
                               float(noise_eps), float(random_eps), float(late_clip), int(seed), _lib.ptr(counter),
                               ctypes.pointer(eps) if eps is not None else None, _lib.ptr(self.init) if reset else None,
                               _lib.ptr(self.obs), _lib.ptr(self.ag), _lib.ptr(self.g), _lib.ptr(self.success))
-        _lib.call("bmi_env_rollout", self._h, ctypes.byref(ra), _lib.stream_ptr())
+        if queue is not None:
+            _lib.call("bmi_env_rollout_queue", self._h, ctypes.byref(ra), int(queue[0]), int(queue[1]), _lib.stream_ptr())
+        else:
+            _lib.call("bmi_env_rollout", self._h, ctypes.byref(ra), _lib.stream_ptr())
         return self.obs, self.ag, self.g, self.success
 
     def get_state(self):

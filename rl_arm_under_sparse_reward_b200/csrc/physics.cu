@@ -127,6 +127,7 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
   float obs[BMI_OBS_DIM + BMI_GOAL_DIM];   // last observation + achieved goal (fused rollout)
   float qik[NL];
   int prof_e;
+  int it_sum;                     // solver iterations since the env-step began (routing key of the task-queue rollout)
 };
 
 struct EnvParams {
@@ -969,6 +970,7 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
 #undef BMI_JOINT_ROWS
 #undef BMI_JOINT_EVENT
   PROF_CNT(s.prof_e, 7, it);
+  if (lane == 0) s.it_sum += it;
   // ---- integrate --------------------------------------------------------------------------------------------------
   const float unew = lane < NU ? s.u[lane] + v0 : 0.f;
   if (lane < NL) {
@@ -1214,6 +1216,93 @@ __device__ __noinline__ Philox4 philox_explore(unsigned long long seed, unsigned
   return philox4x32_10(seed, ctr, kStreamExplore);
 }
 
+// actor parameters inside the transposed flat buffer (bmi_actor_transpose)
+struct PolicyW {
+  const float *Wt1, *b1, *Wt2, *b2, *Wt3, *b3, *Wt4, *b4;
+};
+__device__ __forceinline__ PolicyW policy_weights(const RolloutArgs& ra) {
+  constexpr int Dx = BMI_OBS_DIM + BMI_GOAL_DIM, Da = BMI_ACT_DIM;
+  PolicyW w;
+  w.Wt1 = ra.actor_t;        w.b1 = w.Wt1 + Dx * HID;
+  w.Wt2 = w.b1 + HID;        w.b2 = w.Wt2 + HID * HID;
+  w.Wt3 = w.b2 + HID;        w.b3 = w.Wt3 + HID * HID;
+  w.Wt4 = w.b3 + HID;        w.b4 = w.Wt4 + HID * Da;
+  return w;
+}
+
+// One step of the rollout loop of ddpg_agent.learn() (ddpg_agent.py:111-141) for env e at time t: record obs / ag / g,
+// policy, exploration noise, record the action, env step, new observation into s.obs.
+__device__ __forceinline__ void rollout_step(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
+                                             const RolloutArgs& ra, const PolicyW& pw, unsigned long long ctr0, int n_envs,
+                                             int e, int t, int lane) {
+  constexpr int Do = BMI_OBS_DIM, Dg = BMI_GOAL_DIM, Da = BMI_ACT_DIM, Dx = Do + Dg;
+  const float *Wt1 = pw.Wt1, *b1 = pw.b1, *Wt2 = pw.Wt2, *b2 = pw.b2, *Wt3 = pw.Wt3, *b3 = pw.b3, *Wt4 = pw.Wt4, *b4 = pw.b4;
+  PROF_T0();
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  // ---- record obs / ag / g of step t -----------------------------------------------------------------
+  if (ra.ep_obs) {
+    if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + t) * Do + lane] = s.obs[lane];
+    if (lane < Dg) {
+      ra.ep_ag[((size_t)e * (ra.T + 1) + t) * Dg + lane] = s.obs[Do + lane];
+      ra.ep_g[((size_t)e * ra.T + t) * Dg + lane] = s.goal[lane];
+    }
+  }
+  // ---- policy: normalise -> 3 hidden layers -> tanh head (ddpg_agent.py:113-116) ------------------------
+  if (lane < Do) s.pol.x[lane] = norm_clip(s.obs[lane], ra.o_mean[lane], ra.o_std[lane], ra.clip_range);
+  else if (lane < Dx) s.pol.x[lane] = norm_clip(s.goal[lane - Do], ra.g_mean[lane - Do], ra.g_std[lane - Do], ra.clip_range);
+  __syncwarp();
+  policy_layer(Wt1, b1, s.pol.x, Dx, s.pol.h, lane);
+  policy_layer(Wt2, b2, s.pol.h, HID, s.pol.h, lane);   // in place: every lane has read all inputs before any stores
+  policy_layer(Wt3, b3, s.pol.h, HID, s.pol.h, lane);
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const int k = lane * 8 + kk;
+    const float hk = s.pol.h[k];
+    const float4 w = __ldg(reinterpret_cast<const float4*>(Wt4) + k);
+    z[0] = fmaf(hk, w.x, z[0]); z[1] = fmaf(hk, w.y, z[1]); z[2] = fmaf(hk, w.z, z[2]); z[3] = fmaf(hk, w.w, z[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v = z[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    a[j] = ra.action_max * tanhf(v + __ldg(b4 + j));
+  }
+  if (ra.explore) {  // _select_actions (ddpg_agent.py:174-184): same Philox stream as bmi_select_actions
+    const unsigned long long c = ctr0 + (unsigned long long)t * (unsigned long long)n_envs + (unsigned long long)e;
+    const Philox4 pg = philox_explore(ra.seed, 3 * c);
+    const Philox4 pu = philox_explore(ra.seed, 3 * c + 1);
+    const Philox4 pb = philox_explore(ra.seed, 3 * c + 2);
+    const bool take_random = u24(pb.v[0]) < ra.random_eps;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pair = (j >> 1) & 1;
+      const float u1 = 1.0f - u24(pg.v[2 * pair]);
+      const float u2 = u24(pg.v[2 * pair + 1]);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      const float gz = (j & 1) ? rad * sinf(6.28318530717958647692f * u2) : rad * cosf(6.28318530717958647692f * u2);
+      float v = a[j] + ra.noise_eps * ra.action_max * gz;
+      v = fminf(fmaxf(v, -ra.action_max), ra.action_max);
+      const float rv = -ra.action_max + 2.0f * ra.action_max * u24(pu.v[j & 3]);
+      if (take_random) v = rv;
+      if (ra.late_clip > 0.f) v = fminf(fmaxf(v, -ra.late_clip), ra.late_clip);
+      a[j] = v;
+    }
+  }
+  if (ra.ep_act && lane < Da) {
+    float v = a[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) if (lane == j) v = a[j];
+    ra.ep_act[((size_t)e * ra.T + t) * Da + lane] = v;
+  }
+  __syncwarp();
+  // ---- env step (the sub-step solves run on the block's solver warp) -------------------------------------------
+  PROF_ADD(e, 0);
+  env_step_warp(s, ep, model_g, a, lane, e);
+  observe(s, lane, s.obs, s.obs + Do);
+}
+
 __global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
 rollout_kernel(const float* __restrict__ model_g, unsigned model_bytes, EnvParams ep, int n_envs,
                float* __restrict__ state, RolloutArgs ra) {
@@ -1241,82 +1330,10 @@ rollout_kernel(const float* __restrict__ model_g, unsigned model_bytes, EnvParam
   }
   load_state(s, st, lane);
   observe(s, lane, s.obs, s.obs + BMI_OBS_DIM);
-  constexpr int Do = BMI_OBS_DIM, Dg = BMI_GOAL_DIM, Da = BMI_ACT_DIM, Dx = Do + Dg;
-  const float* Wt1 = ra.actor_t;
-  const float* b1 = Wt1 + Dx * HID;
-  const float* Wt2 = b1 + HID;
-  const float* b2 = Wt2 + HID * HID;
-  const float* Wt3 = b2 + HID;
-  const float* b3 = Wt3 + HID * HID;
-  const float* Wt4 = b3 + HID;
-  const float* b4 = Wt4 + HID * Da;
+  constexpr int Do = BMI_OBS_DIM, Dg = BMI_GOAL_DIM;
+  const PolicyW pw = policy_weights(ra);
   const unsigned long long ctr0 = ra.explore ? *ra.counter : 0ull;
-  for (int t = 0; t < ra.T; ++t) {
-    PROF_T0();
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    // ---- record obs / ag / g of step t -----------------------------------------------------------------
-    if (ra.ep_obs) {
-      if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + t) * Do + lane] = s.obs[lane];
-      if (lane < Dg) {
-        ra.ep_ag[((size_t)e * (ra.T + 1) + t) * Dg + lane] = s.obs[Do + lane];
-        ra.ep_g[((size_t)e * ra.T + t) * Dg + lane] = s.goal[lane];
-      }
-    }
-    // ---- policy: normalise -> 3 hidden layers -> tanh head (ddpg_agent.py:113-116) ------------------------
-    if (lane < Do) s.pol.x[lane] = norm_clip(s.obs[lane], ra.o_mean[lane], ra.o_std[lane], ra.clip_range);
-    else if (lane < Dx) s.pol.x[lane] = norm_clip(s.goal[lane - Do], ra.g_mean[lane - Do], ra.g_std[lane - Do], ra.clip_range);
-    __syncwarp();
-    policy_layer(Wt1, b1, s.pol.x, Dx, s.pol.h, lane);
-    policy_layer(Wt2, b2, s.pol.h, HID, s.pol.h, lane);   // in place: every lane has read all inputs before any stores
-    policy_layer(Wt3, b3, s.pol.h, HID, s.pol.h, lane);
-    float z[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      const int k = lane * 8 + kk;
-      const float hk = s.pol.h[k];
-      const float4 w = __ldg(reinterpret_cast<const float4*>(Wt4) + k);
-      z[0] = fmaf(hk, w.x, z[0]); z[1] = fmaf(hk, w.y, z[1]); z[2] = fmaf(hk, w.z, z[2]); z[3] = fmaf(hk, w.w, z[3]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v = z[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-      a[j] = ra.action_max * tanhf(v + __ldg(b4 + j));
-    }
-    if (ra.explore) {  // _select_actions (ddpg_agent.py:174-184): same Philox stream as bmi_select_actions
-      const unsigned long long c = ctr0 + (unsigned long long)t * (unsigned long long)n_envs + (unsigned long long)e;
-      const Philox4 pg = philox_explore(ra.seed, 3 * c);
-      const Philox4 pu = philox_explore(ra.seed, 3 * c + 1);
-      const Philox4 pb = philox_explore(ra.seed, 3 * c + 2);
-      const bool take_random = u24(pb.v[0]) < ra.random_eps;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int pair = (j >> 1) & 1;
-        const float u1 = 1.0f - u24(pg.v[2 * pair]);
-        const float u2 = u24(pg.v[2 * pair + 1]);
-        const float rad = sqrtf(-2.0f * logf(u1));
-        const float gz = (j & 1) ? rad * sinf(6.28318530717958647692f * u2) : rad * cosf(6.28318530717958647692f * u2);
-        float v = a[j] + ra.noise_eps * ra.action_max * gz;
-        v = fminf(fmaxf(v, -ra.action_max), ra.action_max);
-        const float rv = -ra.action_max + 2.0f * ra.action_max * u24(pu.v[j & 3]);
-        if (take_random) v = rv;
-        if (ra.late_clip > 0.f) v = fminf(fmaxf(v, -ra.late_clip), ra.late_clip);
-        a[j] = v;
-      }
-    }
-    if (ra.ep_act && lane < Da) {
-      float v = a[0];
-#pragma unroll
-      for (int j = 1; j < 4; ++j) if (lane == j) v = a[j];
-      ra.ep_act[((size_t)e * ra.T + t) * Da + lane] = v;
-    }
-    __syncwarp();
-    // ---- env step (the sub-step solves run on the block's solver warp) -------------------------------------------
-    PROF_ADD(e, 0);
-    env_step_warp(s, ep, model_g, a, lane, e);
-    observe(s, lane, s.obs, s.obs + Do);
-  }
+  for (int t = 0; t < ra.T; ++t) rollout_step(s, ep, model_g, ra, pw, ctr0, n_envs, e, t, lane);
   if (ra.ep_obs) {
     if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + ra.T) * Do + lane] = s.obs[lane];
     if (lane < Dg) ra.ep_ag[((size_t)e * (ra.T + 1) + ra.T) * Dg + lane] = s.obs[Do + lane];
@@ -1326,6 +1343,128 @@ rollout_kernel(const float* __restrict__ model_g, unsigned model_bytes, EnvParam
   if (ra.g && lane < Dg) ra.g[(size_t)e * Dg + lane] = s.goal[lane];
   if (ra.success && lane == 0) ra.success[e] = goal_dist(s) < P(s, MP_DIST_THRESHOLD) ? 1.f : 0.f;
   store_state(s, st, lane);
+}
+
+// ---- task-queue rollout (EXPERIMENTAL, Args.queue_rollout) ---------------------------------------------------------
+// Same episodes as rollout_kernel, bit for bit (every env-step is computed by rollout_step from the env's own state),
+// but a warp is not bound to an env: a task is ONE env-step (env, t).  q.word[env] packs
+//   bit 31: claimed   bits 30..16: solver iterations of the env's last step (routing key)   bits 15..0: steps done.
+// A free warp scans the words, claims an unclaimed env with steps left (atomicCAS), loads its 48-float state and last
+// observation from global memory, runs the step, stores, and releases the word with the new key.  The blocks
+// [0, express_blocks) are "express": only express_warps of their warps run, and they pick the env with the LARGEST key;
+// all other warps pick the smallest key (ties: fewest steps done).  An env whose hand rests on the table (2-3x the
+// solver iterations, for the whole episode) therefore migrates to an express SM where it shares a sub-partition with at
+// most one other warp, instead of setting the launch time from a fully loaded SM.
+// No warp ever waits for another one: a warp exits when no unclaimed env has steps left.
+struct QueueArgs {
+  unsigned* word;        // [n_envs]
+  float* obs_cache;      // [n_envs][BMI_OBS_DIM + BMI_GOAL_DIM]: observation + achieved goal after the env's last step
+  int express_blocks, express_warps;
+};
+
+__global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
+rollout_queue_kernel(const float* __restrict__ model_g, unsigned model_bytes, EnvParams ep, int n_envs,
+                     float* __restrict__ state, RolloutArgs ra, QueueArgs q) {
+  BlockSmem& bs = *reinterpret_cast<BlockSmem*>(bmi_dyn_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  block_begin(bs, model_g, model_bytes);
+  const bool express = (int)blockIdx.x < q.express_blocks;
+  if (express && warp >= q.express_warps) return;
+  Smem& s = bs.sw[warp];
+  constexpr int Do = BMI_OBS_DIM, Dg = BMI_GOAL_DIM;
+  const PolicyW pw = policy_weights(ra);
+  const unsigned long long ctr0 = ra.explore ? *ra.counter : 0ull;
+  const unsigned T = (unsigned)ra.T;
+  // start the scan at a warp-specific offset so that simultaneous pickers do not all fight for the same entry
+  const int scan0 = (int)(((blockIdx.x * WARPS + warp) * 97u) % (unsigned)n_envs);
+  while (true) {
+    // ---- pick: best unclaimed env with steps left ------------------------------------------------------------------
+    unsigned best_key = 0u;   // larger = better; 0 = nothing found
+    int best_env = -1;
+    for (int i = lane; i < n_envs; i += 32) {
+      int e = scan0 + i;
+      if (e >= n_envs) e -= n_envs;
+      const unsigned w = __ldcg(q.word + e);
+      const unsigned done = w & 0xffffu, cost = (w >> 16) & 0x7fffu;
+      if ((w >> 31) == 0u && done < T) {
+        // express: most expensive first; bulk: cheapest first, then the env that is furthest behind
+        const unsigned key = express ? (1u + (cost << 16) + (0xffffu - done)) : (1u + ((0x7fffu - cost) << 16) + (0xffffu - done));
+        if (key > best_key) { best_key = key; best_env = e; }
+      }
+    }
+    const unsigned top = __reduce_max_sync(FULL, best_key);
+    if (top == 0u) break;   // nothing left to start (envs in flight are continued by the warps that hold them)
+    const int src = __ffs(__ballot_sync(FULL, best_key == top)) - 1;
+    const int e = __shfl_sync(FULL, best_env, src);
+    unsigned mine = 0u;
+    int ok = 0;
+    if (lane == 0) {
+      mine = __ldcg(q.word + e);
+      ok = (mine >> 31) == 0u && (mine & 0xffffu) < T && atomicCAS(q.word + e, mine, mine | 0x80000000u) == mine;
+    }
+    ok = __shfl_sync(FULL, ok, 0);
+    if (!ok) continue;      // somebody else was faster: rescan
+    const int t = (int)(__shfl_sync(FULL, mine, 0) & 0xffffu);
+    __threadfence();        // acquire: the previous holder's state / observation stores
+    // ---- load the env ------------------------------------------------------------------------------------------------
+    float* st = state + (size_t)e * BMI_ENV_STATE_DIM;
+    if (t == 0 && ra.init != nullptr) {  // reset (bmirobot_env_push_F.py:110-165)
+      const float* in = ra.init + (size_t)e * 8;
+      for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {
+        float v = 0.f;
+        if (i >= ST_BPOS && i < ST_BPOS + 3) v = in[i - ST_BPOS];
+        else if (i == ST_BQUAT + 2 || i == ST_BQUAT + 3) {
+          float sy, cy;
+          sincos_compact(0.5f * in[3], &sy, &cy);
+          v = i == ST_BQUAT + 2 ? sy : cy;
+        }
+        else if (i >= ST_GOAL && i < ST_GOAL + 3) v = in[4 + i - ST_GOAL];
+        st[i] = v;
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {   // load_state through L2 (the previous holder may sit on another SM)
+      const float v = __ldcg(st + i);
+      if (i < ST_QD) s.q[i - ST_Q] = v;
+      else if (i < ST_QT) s.qd[i - ST_QD] = v;
+      else if (i < ST_BPOS) s.qt[i - ST_QT] = v;
+      else if (i < ST_BQUAT) s.bp[i - ST_BPOS] = v;
+      else if (i < ST_BVEL) s.bq[i - ST_BQUAT] = v;
+      else if (i < ST_BANG) s.bv[i - ST_BVEL] = v;
+      else if (i < ST_GOAL) s.bw[i - ST_BANG] = v;
+      else if (i < ST_PAD) s.goal[i - ST_GOAL] = v;
+    }
+    __syncwarp();
+    if (t == 0) observe(s, lane, s.obs, s.obs + Do);
+    else {
+      if (lane < Do + Dg) s.obs[lane] = __ldcg(q.obs_cache + (size_t)e * (Do + Dg) + lane);
+      __syncwarp();
+    }
+    if (lane == 0) s.it_sum = 0;
+    __syncwarp();
+    // ---- the step -----------------------------------------------------------------------------------------------------
+    rollout_step(s, ep, model_g, ra, pw, ctr0, n_envs, e, t, lane);
+    // ---- store, release ------------------------------------------------------------------------------------------------
+    store_state(s, st, lane);
+    if (lane < Do + Dg) q.obs_cache[(size_t)e * (Do + Dg) + lane] = s.obs[lane];
+    if (t + 1 == ra.T) {
+      if (ra.ep_obs) {
+        if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + ra.T) * Do + lane] = s.obs[lane];
+        if (lane < Dg) ra.ep_ag[((size_t)e * (ra.T + 1) + ra.T) * Dg + lane] = s.obs[Do + lane];
+      }
+      if (ra.obs && lane < Do) ra.obs[(size_t)e * Do + lane] = s.obs[lane];
+      if (ra.ag && lane < Dg) ra.ag[(size_t)e * Dg + lane] = s.obs[Do + lane];
+      if (ra.g && lane < Dg) ra.g[(size_t)e * Dg + lane] = s.goal[lane];
+      if (ra.success && lane == 0) ra.success[e] = goal_dist(s) < P(s, MP_DIST_THRESHOLD) ? 1.f : 0.f;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned cost = (unsigned)min(s.it_sum, 0x7fff);
+      __threadfence();      // release: state / observation before the word
+      atomicExch(q.word + e, (cost << 16) | (unsigned)(t + 1));
+    }
+    __syncwarp();
+  }
 }
 
 // W[out][in] (torch layout) -> Wt[in][out]
@@ -1413,6 +1552,8 @@ struct bmi_env {
   float* state_dev = nullptr;
   int64_t model_floats = 0;
   unsigned model_bytes = 0;     // staged size: the blob rounded up to 16 bytes
+  unsigned* queue_word = nullptr;   // task-queue rollout: one word per env (lazily allocated)
+  float* queue_obs = nullptr;       // ... and the observation cache
 };
 
 extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const void* blob, int64_t bytes) {
@@ -1443,6 +1584,7 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   {  // the env kernels keep ENVW env working sets per block in dynamic shared memory (> 48 KB: opt-in)
     BMI_CUDA_CHECK(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem)));
     BMI_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem)));
+    BMI_CUDA_CHECK(cudaFuncSetAttribute(rollout_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem)));
   }
   bmi_env* h = new bmi_env();
   h->n_envs = n_envs;
@@ -1485,6 +1627,8 @@ extern "C" int bmi_env_destroy(bmi_env* h) {
   if (!h) return BMI_OK;
   if (h->model_dev) cudaFree(h->model_dev);
   if (h->state_dev) cudaFree(h->state_dev);
+  if (h->queue_word) cudaFree(h->queue_word);
+  if (h->queue_obs) cudaFree(h->queue_obs);
   delete h;
   return BMI_OK;
 }
@@ -1553,11 +1697,10 @@ extern "C" int bmi_actor_transpose(const float* actor_params, int32_t obs_dim, i
   return BMI_OK;
 }
 
-extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream_t stream) {
-  BMI_REQUIRE(h && a, "bmi_env_rollout: null pointer");
-  BMI_REQUIRE(a->T > 0 && a->actor_t && a->o_mean && a->o_std && a->g_mean && a->g_std, "bmi_env_rollout: missing policy inputs");
-  BMI_REQUIRE(!a->explore || a->counter, "bmi_env_rollout: exploration needs a Philox counter");
-  RolloutArgs ra;
+static int fill_rollout_args(bmi_env* h, const bmi_rollout_args* a, RolloutArgs& ra, const char* who) {
+  BMI_REQUIRE(h && a, "%s: null pointer", who);
+  BMI_REQUIRE(a->T > 0 && a->actor_t && a->o_mean && a->o_std && a->g_mean && a->g_std, "%s: missing policy inputs", who);
+  BMI_REQUIRE(!a->explore || a->counter, "%s: exploration needs a Philox counter", who);
   ra.T = a->T; ra.explore = a->explore; ra.actor_t = a->actor_t;
   ra.o_mean = a->o_mean; ra.o_std = a->o_std; ra.g_mean = a->g_mean; ra.g_std = a->g_std;
   ra.clip_range = a->clip_range; ra.action_max = a->action_max; ra.noise_eps = a->noise_eps;
@@ -1567,12 +1710,46 @@ extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream
     const bmi_episodes* e = a->episodes;
     BMI_REQUIRE(e->dtype == BMI_F32 && e->T == a->T && e->n_episodes == h->n_envs && e->obs_dim == BMI_OBS_DIM &&
                     e->goal_dim == BMI_GOAL_DIM && e->act_dim == BMI_ACT_DIM,
-                "bmi_env_rollout: episodes must be float32 [n_envs][T(+1)][27|3|3|4]");
+                "%s: episodes must be float32 [n_envs][T(+1)][27|3|3|4]", who);
     ra.ep_obs = (float*)e->obs; ra.ep_ag = (float*)e->ag; ra.ep_g = (float*)e->g; ra.ep_act = (float*)e->actions;
   }
   ra.init = a->init; ra.obs = a->obs; ra.ag = a->ag; ra.g = a->g; ra.success = a->success;
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream_t stream) {
+  RolloutArgs ra;
+  const int rc = fill_rollout_args(h, a, ra, "bmi_env_rollout");
+  if (rc != BMI_OK) return rc;
   cudaStream_t st = as_stream(stream);
   rollout_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->model_bytes, h->ep, h->n_envs, h->state_dev, ra);
+  BMI_LAUNCHED();
+  if (a->explore) {
+    advance_counter_kernel3<<<1, 1, 0, st>>>(a->counter, (uint64_t)a->T * (uint64_t)h->n_envs);
+    BMI_LAUNCHED();
+  }
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_rollout_queue(bmi_env* h, const bmi_rollout_args* a, int32_t express_blocks, int32_t express_warps,
+                                     bmi_stream_t stream) {
+  RolloutArgs ra;
+  const int rc = fill_rollout_args(h, a, ra, "bmi_env_rollout_queue");
+  if (rc != BMI_OK) return rc;
+  const int blocks = (h->n_envs + ENVW - 1) / ENVW;
+  BMI_REQUIRE(a->T < 65536, "bmi_env_rollout_queue: T must be below 65536");
+  BMI_REQUIRE(express_blocks >= 0 && express_blocks < blocks + (blocks == 1) && express_warps >= 1 && express_warps <= ENVW,
+              "bmi_env_rollout_queue: express_blocks must be in [0, %d) and express_warps in [1, %d]", blocks, ENVW);
+  if (blocks == 1) express_blocks = 0;   // a single block must keep all its warps
+  if (!h->queue_word) {
+    BMI_CUDA_CHECK(cudaMalloc(&h->queue_word, (size_t)h->n_envs * sizeof(unsigned)));
+    BMI_CUDA_CHECK(cudaMalloc(&h->queue_obs, (size_t)h->n_envs * (BMI_OBS_DIM + BMI_GOAL_DIM) * sizeof(float)));
+  }
+  cudaStream_t st = as_stream(stream);
+  BMI_CUDA_CHECK(cudaMemsetAsync(h->queue_word, 0, (size_t)h->n_envs * sizeof(unsigned), st));
+  QueueArgs q;
+  q.word = h->queue_word; q.obs_cache = h->queue_obs; q.express_blocks = express_blocks; q.express_warps = express_warps;
+  rollout_queue_kernel<<<blocks, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->model_bytes, h->ep, h->n_envs, h->state_dev, ra, q);
   BMI_LAUNCHED();
   if (a->explore) {
     advance_counter_kernel3<<<1, 1, 0, st>>>(a->counter, (uint64_t)a->T * (uint64_t)h->n_envs);

@@ -208,7 +208,9 @@ class ddpg_agent:
                   _lib.ptr(self._actor_t), _lib.stream_ptr())
         self.vec.rollout(self.T, self._actor_t, self.o_norm, self.g_norm, self.args.clip_range, explore,
                          noise_eps=self.args.noise_eps, random_eps=self.args.random_eps, late_clip=late_clip,
-                         seed=self._seed, counter=self._ctr_explore, episodes=self.ep if explore else None)
+                         seed=self._seed, counter=self._ctr_explore, episodes=self.ep if explore else None,
+                         queue=((int(getattr(self.args, 'queue_express_blocks', 0)), int(getattr(self.args, 'queue_express_warps', 8)))
+                                if getattr(self.args, 'queue_rollout', False) else None))
 
     def rollout(self, epoch=0):
         """One batch of R simultaneous episodes (ddpg_agent.py:103-141); fills self.ep.  Default: the fused

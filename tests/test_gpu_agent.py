@@ -152,3 +152,20 @@ def test_pick_task_cycle_with_demo_preload(tmp_path, golden_dir):
     z = ag.ep['ag'][:, 5, 2]
     assert ((z - 0.215).abs() < 5e-3).float().mean() > 0.6
     assert (z > 0.19).all() and (z < 0.30).all()
+
+
+@pytest.mark.parametrize("express", [(0, 8), (1, 4)])
+def test_task_queue_rollout_reproduces_the_fused_rollout_bit_for_bit(tmp_path, express):
+    """EXPERIMENTAL bmi_env_rollout_queue: env-steps are scheduled dynamically (any warp, any SM, express blocks for
+    the expensive envs) but every step is computed from the env's own state, so the episodes must be identical."""
+    ag1, _ = _agent(tmp_path, n_envs=96)
+    ag2, _ = _agent(tmp_path, n_envs=96, queue_rollout=True, queue_express_blocks=express[0], queue_express_warps=express[1])
+    ag2.actor_network.flat.copy_(ag1.actor_network.flat)
+    for ag in (ag1, ag2):
+        ag.rollout(0)
+        ag.rollout(0)          # second batch: fresh placements, Philox counters advanced
+    torch.cuda.synchronize()
+    for k in ("obs", "ag", "g", "actions"):
+        assert torch.equal(ag1.ep[k], ag2.ep[k]), k
+    assert torch.equal(ag1.vec.success, ag2.vec.success) and torch.equal(ag1.vec.obs, ag2.vec.obs)
+    assert torch.equal(ag1.vec.get_state(), ag2.vec.get_state())

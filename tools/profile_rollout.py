@@ -9,7 +9,11 @@ from rl_arm_under_sparse_reward_b200.train import get_env_params
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 100
-a = Args(); a.add_demo, a.verbose, a.n_envs, a.buffer_size, a.save_dir = False, False, n, 8192 * 100, "/tmp/bmi_prof/"
+a = Args()
+if os.environ.get("BMI_QUEUE"):   # "express_blocks,express_warps": the experimental task-queue rollout
+    a.queue_rollout = True
+    a.queue_express_blocks, a.queue_express_warps = [int(x) for x in os.environ["BMI_QUEUE"].split(",")]
+a.add_demo, a.verbose, a.n_envs, a.buffer_size, a.save_dir = False, False, n, 8192 * 100, "/tmp/bmi_prof/"
 torch.manual_seed(125)
 env = BmiVecEnv(n, seed=125)
 p = get_env_params(env); p['max_timesteps'] = T
