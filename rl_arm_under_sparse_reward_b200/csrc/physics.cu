@@ -1297,7 +1297,7 @@ __device__ __forceinline__ void rollout_step(Smem& s, const EnvParams& ep, const
     ra.ep_act[((size_t)e * ra.T + t) * Da + lane] = v;
   }
   __syncwarp();
-  // ---- env step (the sub-step solves run on the block's solver warp) -------------------------------------------
+  // ---- env step -----------------------------------------------------------------------------------------------------
   PROF_ADD(e, 0);
   env_step_warp(s, ep, model_g, a, lane, e);
   observe(s, lane, s.obs, s.obs + Do);
