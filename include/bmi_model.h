@@ -38,7 +38,13 @@ enum {
   MP_PICK_HX = 37, MP_PICK_HY = 38, MP_PICK_HZ = 39, MP_PICK_MASS = 40, MP_PICK_MU = 41,
   MP_DIST_THRESHOLD = 42, MP_JOINT_LIMIT_IMPULSE = 43, MP_BLOCK_MARGIN = 44, MP_TABLE_MARGIN = 45,
   MP_IK_POS_AT_COM = 46, MP_SELF_COLLISION = 47,
-  MP_WARMSTART = 48       /* contact warm-starting factor (Bullet default 0.85); 0 disables */
+  MP_WARMSTART = 48,      /* contact warm-starting factor (Bullet default 0.85); 0 disables */
+  MP_HULL_MARGIN = 49,    /* collision margin of a convex-hull shape (PyBullet URDF meshes: 0.001) */
+  MP_SELF_SPLIT_DIAG = 50,/* 1: Bullet's row diagonal for contacts between two links of one multibody (no cross term) */
+  MP_SWEEP_ALTERNATE = 51,/* 1: non-contact rows are swept backwards on even solver iterations (Bullet) */
+  MP_SELF_NEAR = 53,      /* self-collision pairs closer than this (beyond the margins) still produce a (speculative) row */
+  MP_FULL_HULLS = 54,     /* oracle only: arm-table / arm-block contacts from the full hulls of all links (GJK + EPA) */
+  MP_LIMITS_FIRST = 52    /* 1: joint-limit rows precede the motor rows (order the constraints were created in) */
 };
 
 /* per-link slots (BMI_LINK_STRIDE floats each) */

@@ -28,14 +28,16 @@
 #include <string.h>
 
 #include "../include/bmi_model.h"
+#include "convex_epa.h"
 
 #define NL 9
 #define NU 15 /* generalized velocities: 9 joints + block linear 3 + block angular 3 */
 #define MAX_ROWS 192
-#define MAX_CONTACTS 9       /* contacts per sub-step (same caps as the kernel: csrc/physics.cu MAXC / MAXA) */
-#define MAX_ARM_CONTACTS 6   /* ... of which at most 6 involve an arm link; later candidates are dropped */
+#define MAX_CONTACTS 48      /* storage only: the oracle keeps every contact it finds */
+#define MAX_ARM_CONTACTS 48
 #define MAX_SHAPE_V 32
 #define MAX_SHAPE_P 64
+#define MAX_HULLS 12         /* full-resolution convex hulls of the collision meshes (self-collision, bmo_set_hulls) */
 
 typedef struct {
   int nl, ns;
@@ -45,6 +47,10 @@ typedef struct {
   double s_v[BMI_MAX_SHAPES][MAX_SHAPE_V][3], s_p[BMI_MAX_SHAPES][MAX_SHAPE_P][4], s_c[BMI_MAX_SHAPES][3], s_r[BMI_MAX_SHAPES],
       s_mu[BMI_MAX_SHAPES];
   double P[BMI_MODEL_HDR];
+  /* full convex hulls (every hull vertex of the collision mesh) used by the arm's self-collision */
+  int nh, h_link[MAX_HULLS], h_nv[MAX_HULLS];
+  double* h_v[MAX_HULLS];
+  double h_c[MAX_HULLS][3], h_r[MAX_HULLS], h_mu[MAX_HULLS];
 } Model;
 
 typedef struct {
@@ -341,10 +347,13 @@ typedef struct {
 } Row;
 
 typedef struct {
-  int link;     /* arm link index or -1 (static world) */
+  int link;     /* arm link index of body 2, or -1 (static world) */
   int has_block;/* 1: body 1 is the block */
-  double x[3], n[3], dist, mu;
-  int id;       /* candidate slot: block vertex 0..7 | 8 + 32 shape + hull vertex | 136 + 32 shape + candidate */
+  int link1;    /* self-collision: arm link index of body 1 (>= 0; -1 = the static base link), unused otherwise */
+  int self;     /* 1: contact between two links of the arm */
+  double x[3], n[3], dist, mu;  /* x: contact point (on body 1 for self-collision), n: normal from body 2 towards body 1 */
+  double x2[3]; /* self-collision: witness point on body 2 */
+  int id;       /* candidate slot: block vertex 0..7 | 8 + 32 shape + hull vertex | 136 + 32 shape + candidate | 1000 + 16 hullA + hullB */
 } Contact;
 
 static void block_vertices(const Env* e, const State* s, const double* Rb, double v[8][3]) {
@@ -386,11 +395,63 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
     int n = select_deepest(d, 8, m->P[MP_TABLE_MARGIN], 4, sel);
     for (int i = 0; i < n; ++i) {
       Contact* c = &C[nc++];
-      c->link = -1; c->has_block = 1; c->id = sel[i]; v3cpy(c->x, bv[sel[i]]); v3set(c->n, 0, 0, 1);
+      c->link = -1; c->link1 = -1; c->self = 0; c->has_block = 1; c->id = sel[i]; v3cpy(c->x, bv[sel[i]]); v3set(c->n, 0, 0, 1);
       c->dist = d[sel[i]]; c->mu = e->bmu * m->P[MP_MU_TABLE];
     }
   }
   double brad = v3norm(e->bh);
+  if (m->P[MP_FULL_HULLS] > 0.5 && m->nh > 0) {
+    /* faithful geometry: every arm link's full convex hull against the table top and against the block (box hull);
+     * narrow phase = closest points / penetration depth (GJK + EPA), one point per pair and sub-step, Bullet's margins
+     * (hull MP_HULL_MARGIN; the block is a btBoxShape whose margin is inside its extents) */
+    const double margin = m->P[MP_HULL_MARGIN];
+    double bl[24];
+    for (int i = 0; i < 8; ++i) { bl[3 * i] = (i & 1 ? 1 : -1) * e->bh[0]; bl[3 * i + 1] = (i & 2 ? 1 : -1) * e->bh[1]; bl[3 * i + 2] = (i & 4 ? 1 : -1) * e->bh[2]; }
+    Cvx B; B.nv = 8; B.v = bl; memcpy(B.R, Rb, sizeof(Rb)); v3cpy(B.p, s->bp);
+    for (int h = 0; h < m->nh; ++h) {
+      int l = m->h_link[h];
+      if (l < 0) continue;
+      Cvx A; A.nv = m->h_nv[h]; A.v = m->h_v[h]; memcpy(A.R, k->R[l], sizeof(A.R)); v3cpy(A.p, k->p[l]);
+      /* table: the two deepest hull vertices below the contact margin */
+      {
+        double cw[3], t[3];
+        m3vec(t, A.R, m->h_c[h]); v3add(cw, A.p, t);
+        if (cw[2] - m->h_r[h] - margin < tz + m->P[MP_CONTACT_MARGIN]) {
+          int b0 = -1, b1 = -1; double d0 = 1e30, d1 = 1e30;
+          for (int i = 0; i < A.nv; ++i) {
+            double z = A.R[6] * A.v[3 * i] + A.R[7] * A.v[3 * i + 1] + A.R[8] * A.v[3 * i + 2] + A.p[2] - margin - tz;
+            if (z < d0) { d1 = d0; b1 = b0; d0 = z; b0 = i; } else if (z < d1) { d1 = z; b1 = i; }
+          }
+          int sel[2] = {b0 < b1 ? b0 : b1, b0 < b1 ? b1 : b0}; double dd[2] = {b0 < b1 ? d0 : d1, b0 < b1 ? d1 : d0};
+          for (int i = 0; i < 2; ++i) if (sel[i] >= 0 && dd[i] < m->P[MP_CONTACT_MARGIN] && nc < MAX_CONTACTS) {
+            Contact* c = &C[nc++];
+            double w[3]; m3vec(w, A.R, A.v + 3 * sel[i]); v3add(c->x, A.p, w); c->x[2] -= margin;
+            c->link = l; c->link1 = -1; c->self = 0; c->has_block = 0; c->id = 8 + 1024 * (h + 1) + sel[i]; v3set(c->n, 0, 0, 1);
+            c->dist = dd[i]; c->mu = m->h_mu[h] * m->P[MP_MU_TABLE];
+          }
+        }
+      }
+      /* block */
+      double ca[3], t[3], d[3];
+      m3vec(t, A.R, m->h_c[h]); v3add(ca, A.p, t); v3sub(d, ca, s->bp);
+      if (v3norm(d) > m->h_r[h] + brad + margin + m->P[MP_SELF_NEAR]) continue;
+      double n[3], pa[3], pb[3];
+      double depth = epa_penetration(&B, &A, n, pa, pb);   /* body 1 = block (A of the EPA), body 2 = link */
+      if (depth < 0) {
+        double gap = gjk_distance(&B, &A, pa, pb);
+        if (gap < 0 || gap > margin + m->P[MP_SELF_NEAR]) continue;
+        for (int r = 0; r < 3; ++r) n[r] = -(pa[r] - pb[r]) / gap;
+        depth = -gap;
+      }
+      if (nc >= MAX_CONTACTS) break;
+      Contact* c = &C[nc++];
+      c->link = l; c->link1 = -1; c->self = 0; c->has_block = 1; c->id = 500 + h;
+      for (int r = 0; r < 3; ++r) { c->n[r] = -n[r]; c->x[r] = pb[r]; }   /* Bullet takes the point on body B; both sides use it here */
+      c->dist = -(depth + margin);
+      c->mu = e->bmu * m->h_mu[h];
+    }
+    return nc;
+  }
   for (int sidx = 0; sidx < m->ns; ++sidx) {
     int l = m->s_link[sidx], nv = m->s_nv[sidx], np = m->s_np[sidx];
     double wv[MAX_SHAPE_V][3];
@@ -404,7 +465,7 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
       for (int i = 0; i < n && nc < MAX_CONTACTS && na < MAX_ARM_CONTACTS; ++i) {
         Contact* c = &C[nc++];
         ++na;
-        c->link = l; c->has_block = 0; c->id = 8 + 32 * sidx + sel[i]; v3cpy(c->x, wv[sel[i]]); v3set(c->n, 0, 0, 1);
+        c->link = l; c->link1 = -1; c->self = 0; c->has_block = 0; c->id = 8 + 32 * sidx + sel[i]; v3cpy(c->x, wv[sel[i]]); v3set(c->n, 0, 0, 1);
         c->dist = d[sel[i]]; c->mu = m->s_mu[sidx] * m->P[MP_MU_TABLE];
       }
     }
@@ -447,12 +508,69 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
       int ci = sel[i];
       Contact* c = &C[nc++];
       ++na;
-      c->link = l; c->has_block = 1; c->id = 136 + 32 * sidx + ci;
+      c->link = l; c->link1 = -1; c->self = 0; c->has_block = 1; c->id = 136 + 32 * sidx + ci;
       v3cpy(c->x, ci < 8 ? bv[ci] : wv[ci - 8]);
       v3cpy(c->n, nrm[ci]); /* normal from the link (body 2) towards the block (body 1) */
       c->dist = d[ci]; c->mu = e->bmu * m->s_mu[sidx];
     }
   }
+  return nc;
+}
+
+/* Self-collision of the arm (bmirobot.py:58 flags=9 -> URDF_USE_SELF_COLLISION, Bullet's default of that flag: every
+ * pair of links collides except a link with its DIRECT parent; links rigidly attached to the fixed base are static and
+ * do not collide with each other).  Narrow phase = penetration depth of the two convex hulls (GJK + EPA as in Bullet's
+ * btGjkEpaPenetrationDepthSolver, convex_epa.h), one point per pair and sub-step; the hulls carry Bullet's collision
+ * margin (MP_HULL_MARGIN per shape).  Only penetrating pairs produce a row. */
+static int hull_parent_link(const Model* m, int hl) { return hl < 0 ? -2 : m->parent[hl]; }
+static int find_self_contacts(const Env* e, const Kin* k, Contact* C, int nc) {
+  const Model* m = &e->m;
+  const double margin = m->P[MP_HULL_MARGIN];
+  for (int a = 0; a < m->nh; ++a)
+    for (int b = a + 1; b < m->nh; ++b) {
+      int la = m->h_link[a], lb = m->h_link[b];
+      if (hull_parent_link(m, lb) == la || hull_parent_link(m, la) == lb) continue; /* parent-child pairs are filtered */
+      if (la < 0 && lb < 0) continue;
+      Cvx A, B;
+      const Cvx* cv[2] = {&A, &B};
+      const int hl[2] = {a, b};
+      for (int s = 0; s < 2; ++s) {
+        Cvx* c = s == 0 ? &A : &B;
+        int l = m->h_link[hl[s]];
+        c->nv = m->h_nv[hl[s]]; c->v = m->h_v[hl[s]];
+        if (l >= 0) { memcpy(c->R, k->R[l], sizeof(c->R)); v3cpy(c->p, k->p[l]); }
+        else { /* right_link1: rigidly attached to the fixed base; link 0's joint origin is expressed in its frame */
+          double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+          memcpy(c->R, I, sizeof(I));
+          v3set(c->p, m->P[MP_BASE_PX], m->P[MP_BASE_PY], m->P[MP_BASE_PZ]);
+        }
+      }
+      (void)cv;
+      /* broadphase: bounding spheres */
+      double ca[3], cb[3], t[3], d[3];
+      m3vec(t, A.R, m->h_c[a]); v3add(ca, A.p, t);
+      m3vec(t, B.R, m->h_c[b]); v3add(cb, B.p, t);
+      v3sub(d, ca, cb);
+      if (v3norm(d) > m->h_r[a] + m->h_r[b] + 2 * margin) continue;
+      double n[3], pa[3], pb[3];
+      double depth = epa_penetration(&A, &B, n, pa, pb);
+      if (depth < 0) {
+        /* separated cores: Bullet still reports the closest points while the gap is below the two margins plus the
+         * manifold's contact breaking threshold; such a row only limits the approach velocity (rhs -= dist / dt) */
+        double gap = gjk_distance(&A, &B, pa, pb);
+        if (gap < 0 || gap > 2 * margin + m->P[MP_SELF_NEAR]) continue;
+        for (int r = 0; r < 3; ++r) n[r] = -(pa[r] - pb[r]) / gap;   /* same sign convention as the EPA normal */
+        depth = -gap;
+      }
+      if (nc >= MAX_CONTACTS) break;
+      Contact* c = &C[nc++];
+      /* EPA on A - B: translating A by -n * depth separates the hulls, so the normal from B (body 2) towards A (body 1) is -n */
+      c->link1 = la; c->link = lb; c->self = 1; c->has_block = 0; c->id = 1000 + 16 * a + b;
+      for (int r = 0; r < 3; ++r) { c->n[r] = -n[r]; c->x[r] = pa[r] - margin * n[r] * 0 ; c->x2[r] = pb[r]; }
+      c->dist = -(depth + 2 * margin);
+      c->mu = m->h_mu[a] * m->h_mu[b];
+      if (c->mu > 10.0) c->mu = 10.0; /* Bullet calculateCombinedFriction clamps the product to 10 */
+    }
   return nc;
 }
 
@@ -472,6 +590,18 @@ static void plane_space(const double* n, double* p, double* q) {
 /* fill J for direction dir at contact c (body 1 = block and/or body 2 = link; world static) */
 static void contact_jacobian(const Env* e, const State* s, const Kin* k, const Contact* c, const double* dir, double* J) {
   memset(J, 0, sizeof(double) * NU);
+  if (c->self) { /* self-collision: body 1 = link1 at x, body 2 = link at x2 */
+    double Jp[27];
+    if (c->link1 >= 0) {
+      point_jacobian(&e->m, k, c->link1, c->x, Jp);
+      for (int j = 0; j < NL; ++j) J[j] += dir[0] * Jp[j] + dir[1] * Jp[9 + j] + dir[2] * Jp[18 + j];
+    }
+    if (c->link >= 0) {
+      point_jacobian(&e->m, k, c->link, c->x2, Jp);
+      for (int j = 0; j < NL; ++j) J[j] -= dir[0] * Jp[j] + dir[1] * Jp[9 + j] + dir[2] * Jp[18 + j];
+    }
+    return;
+  }
   if (c->has_block) {
     double r[3], t[3];
     v3sub(r, c->x, s->bp);
@@ -492,6 +622,25 @@ static void apply_minv(const Env* e, const double* Lm, const double* Ib_inv_worl
   m3vec(W + 12, Ib_inv_world, J + 12);
 }
 
+static double dotn(const double* a, const double* b, int n);
+/* Bullet's diagonal for a row between two links of the SAME multibody (btMultiBodyConstraintSolver::
+ * setupMultiBodyContactConstraint): jacDiagABInv = 1 / (J_A M^-1 J_A^T + J_B M^-1 J_B^T) -- the two sides are treated as
+ * if they were separate bodies, the cross term -2 J_A M^-1 J_B^T is not included.  For neighbouring links of one chain
+ * this is far larger than the true diagonal, i.e. the row is strongly under-relaxed and does not converge within the
+ * iteration budget: the arm's permanent self-contacts are soft because of it. */
+static double self_contact_split_diag(const Env* e, const Kin* k, const double* Lm, const Contact* c, const double* dir) {
+  double d = 0;
+  for (int side = 0; side < 2; ++side) {
+    int l = side == 0 ? c->link1 : c->link;
+    if (l < 0) continue;
+    double Jp[27], J[NL], W[NL];
+    point_jacobian(&e->m, k, l, side == 0 ? c->x : c->x2, Jp);
+    for (int j = 0; j < NL; ++j) J[j] = dir[0] * Jp[j] + dir[1] * Jp[9 + j] + dir[2] * Jp[18 + j];
+    chol9_solve(Lm, J, W);
+    d += dotn(J, W, NL);
+  }
+  return d;
+}
 static double dotn(const double* a, const double* b, int n) { double s = 0; for (int i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
 
 /* one simulation sub-step (Bullet btMultiBodyDynamicsWorld::stepSimulation restated) */
@@ -567,6 +716,7 @@ static void substep(Env* e, State* s) {
   const int n_noncontact = nr;
   Contact C[MAX_CONTACTS];
   int nc = find_contacts(e, s, &k, C);
+  if (m->P[MP_SELF_COLLISION] > 0.5) nc = find_self_contacts(e, &k, C, nc);
   int normal_row[MAX_CONTACTS];
   for (int ci = 0; ci < nc; ++ci) { /* normal rows */
     Row* r = &rows[nr];
@@ -574,6 +724,7 @@ static void substep(Env* e, State* s) {
     contact_jacobian(e, s, &k, &C[ci], C[ci].n, r->J);
     apply_minv(e, Lm, Ibinv, r->J, r->W);
     r->inv_diag = 1.0 / dotn(r->J, r->W, NU);
+    if (C[ci].self && m->P[MP_SELF_SPLIT_DIAG] > 0.5) r->inv_diag = 1.0 / self_contact_split_diag(e, &k, Lm, &C[ci], C[ci].n);
     double rel = dotn(r->J, u, NU);
     double pen = C[ci].dist + m->P[MP_LINEAR_SLOP];
     double pos_err = 0, vel_err = -rel;
@@ -592,6 +743,7 @@ static void substep(Env* e, State* s) {
       contact_jacobian(e, s, &k, &C[ci], d == 0 ? t1 : t2, r->J);
       apply_minv(e, Lm, Ibinv, r->J, r->W);
       r->inv_diag = 1.0 / dotn(r->J, r->W, NU);
+      if (C[ci].self && m->P[MP_SELF_SPLIT_DIAG] > 0.5) r->inv_diag = 1.0 / self_contact_split_diag(e, &k, Lm, &C[ci], d == 0 ? t1 : t2);
       r->rhs = -dotn(r->J, u, NU) * r->inv_diag;
       r->friction_of = normal_row[ci]; r->mu = C[ci].mu;
     }
@@ -621,7 +773,10 @@ static void substep(Env* e, State* s) {
   int it;
   for (it = 0; it < max_it; ++it) {
     double resid = 0;
-    for (int ri = 0; ri < n_normal_end; ++ri) {
+    for (int rj = 0; rj < n_normal_end; ++rj) {
+      /* Bullet sweeps the non-contact rows backwards on even iterations (btMultiBodyConstraintSolver::solveSingleIteration) */
+      int ri = rj;
+      if (rj < n_noncontact && m->P[MP_SWEEP_ALTERNATE] > 0.5 && (it & 1) == 0) ri = n_noncontact - 1 - rj;
       Row* r = &rows[ri];
       double d = r->rhs - dotn(r->J, dv, NU) * r->inv_diag;
       double sum = r->lambda + d;
@@ -659,7 +814,6 @@ static void substep(Env* e, State* s) {
     s->wl[ci][1] = rows[n_normal_end + 2 * ci].lambda;
     s->wl[ci][2] = rows[n_normal_end + 2 * ci + 1].lambda;
   }
-  (void)n_noncontact;
   /* ---- integrate ---- */
   for (int i = 0; i < NL; ++i) { s->qd[i] = u[i] + dv[i]; s->q[i] += dt * s->qd[i]; }
   for (int a = 0; a < 3; ++a) { s->bv[a] = u[9 + a] + dv[9 + a]; s->bw[a] = u[12 + a] + dv[12 + a]; s->bp[a] += dt * s->bv[a]; }
@@ -735,7 +889,40 @@ void* bmo_create(const float* blob, int64_t n, int task) {
   h->st.bq[3] = 1;
   return h;
 }
-void bmo_destroy(void* hp) { free(hp); }
+void bmo_destroy(void* hp) {
+  Handle* h = (Handle*)hp;
+  for (int i = 0; i < h->env.m.nh; ++i) free(h->env.m.h_v[i]);
+  free(hp);
+}
+/* full-resolution hulls: data = [n_hulls, then per hull: link (-1 = right_link1, rigid with the base), friction, n_verts,
+ * 3 n_verts coordinates in the link frame] */
+int bmo_set_hulls(void* hp, const float* data, int64_t n) {
+  Model* m = &((Handle*)hp)->env.m;
+  int64_t o = 0;
+  if (n < 1) return -1;
+  int nh = (int)data[o++];
+  if (nh > MAX_HULLS) return -2;
+  for (int i = 0; i < nh; ++i) {
+    if (o + 3 > n) return -3;
+    m->h_link[i] = (int)data[o++]; m->h_mu[i] = data[o++]; m->h_nv[i] = (int)data[o++];
+    int nv = m->h_nv[i];
+    if (o + 3 * (int64_t)nv > n) return -3;
+    m->h_v[i] = (double*)malloc(sizeof(double) * 3 * nv);
+    double lo[3] = {1e30, 1e30, 1e30}, hi[3] = {-1e30, -1e30, -1e30};
+    for (int k = 0; k < 3 * nv; ++k) {
+      double v = data[o++];
+      m->h_v[i][k] = v;
+      if (v < lo[k % 3]) lo[k % 3] = v;
+      if (v > hi[k % 3]) hi[k % 3] = v;
+    }
+    double r = 0;
+    for (int c = 0; c < 3; ++c) m->h_c[i][c] = 0.5 * (lo[c] + hi[c]);
+    for (int k = 0; k < nv; ++k) { double d[3]; v3sub(d, m->h_v[i] + 3 * k, m->h_c[i]); if (v3norm(d) > r) r = v3norm(d); }
+    m->h_r[i] = r;
+  }
+  m->nh = nh;
+  return 0;
+}
 void bmo_set_param(void* hp, int idx, double v) { ((Handle*)hp)->env.m.P[idx] = v; }
 double bmo_get_param(void* hp, int idx) { return ((Handle*)hp)->env.m.P[idx]; }
 
@@ -827,3 +1014,20 @@ void bmo_mass_matrix(void* hp, const double* q, double* M81) {
 }
 
 void bmo_resid_hist(void* hp, double* out256) { memcpy(out256, ((Handle*)hp)->env.resid_hist, sizeof(double) * 256); }
+
+/* debug / tests: contacts of the current state: out[i*12..] = link1, link, has_block, dist, n(3), x(3), mu, id */
+int bmo_contacts(void* hp, double* out, int cap) {
+  Handle* h = (Handle*)hp;
+  Kin k;
+  fk(&h->env.m, h->st.q, &k);
+  Contact C[MAX_CONTACTS];
+  int nc = find_contacts(&h->env, &h->st, &k, C);
+  if (h->env.m.P[MP_SELF_COLLISION] > 0.5) nc = find_self_contacts(&h->env, &k, C, nc);
+  for (int i = 0; i < nc && i < cap; ++i) {
+    double* o = out + 12 * i;
+    o[0] = C[i].link1; o[1] = C[i].link; o[2] = C[i].has_block; o[3] = C[i].dist;
+    for (int a = 0; a < 3; ++a) { o[4 + a] = C[i].n[a]; o[7 + a] = C[i].x[a]; }
+    o[10] = C[i].mu; o[11] = C[i].id;
+  }
+  return nc;
+}

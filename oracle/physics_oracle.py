@@ -8,6 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "libbmi_oracle.so")
 MODEL = os.path.join(os.path.dirname(HERE), "rl_arm_under_sparse_reward_b200", "assets", "bmirobot_model.bin")
+HULLS = os.path.join(os.path.dirname(HERE), "rl_arm_under_sparse_reward_b200", "assets", "bmirobot_hulls.bin")
 _dp = ctypes.POINTER(ctypes.c_double)
 
 
@@ -25,6 +26,10 @@ def _lib():
     lib.bmo_get_param.restype = ctypes.c_double
     lib.bmo_get_param.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.bmo_set_param.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+    lib.bmo_contacts.restype = ctypes.c_int
+    lib.bmo_contacts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    lib.bmo_set_hulls.restype = ctypes.c_int
+    lib.bmo_set_hulls.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     for name, n in (("bmo_destroy", 1), ("bmo_reset", 5), ("bmo_step", 6), ("bmo_get_state", 2), ("bmo_set_state", 2),
                     ("bmo_stats", 2), ("bmo_ik", 4), ("bmo_fk_ee", 4), ("bmo_mass_matrix", 3)):
         getattr(lib, name).argtypes = [ctypes.c_void_p] * n
@@ -46,6 +51,10 @@ class OracleEnv:
         if not self.h:
             raise RuntimeError("oracle: bad model blob " + model_path)
         self.task = task
+        if os.path.exists(HULLS):
+            self.hulls = np.fromfile(HULLS, dtype="<f4")
+            if self.lib.bmo_set_hulls(self.h, _p(self.hulls), self.hulls.shape[0]) != 0:
+                raise RuntimeError("oracle: bad hull file " + HULLS)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -83,6 +92,12 @@ class OracleEnv:
         o = np.zeros(3, dtype=np.int32)
         self.lib.bmo_stats(self.h, _p(o))
         return tuple(int(x) for x in o)
+
+    def contacts(self):
+        """contact list of the current state: rows of [link1, link, has_block, dist, n(3), x(3), mu, id]"""
+        out = np.zeros(48 * 12)
+        n = self.lib.bmo_contacts(self.h, _p(out), 48)
+        return out[:12 * n].reshape(n, 12).copy()
 
     def ik(self, q0, target):
         q0 = np.ascontiguousarray(q0, dtype=np.float64)

@@ -82,17 +82,15 @@ def test_env_placement_draw_order_matches_reference_semantics():
         assert np.allclose(p[:3], [x, y, 0.2]) and np.allclose(p[4:7], [xt, yt, zt])
 
 
-def test_kernel_and_oracle_share_contact_caps_and_model_constants():
-    """The CUDA env kernel and the C oracle must agree on the contact caps (they change the physics when they bind)
-    and on the model-blob layout they both parse."""
+def test_kernel_lane_budget_and_model_constants():
+    """The kernel's solver gives one lane to every contact (lane budget below); the oracle keeps EVERY contact it finds
+    (storage bound only) and takes the kernel's caps as a run-time option of the kernel-vs-oracle tests (bmo_set_caps)."""
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cu = open(os.path.join(root, "rl_arm_under_sparse_reward_b200", "csrc", "physics.cu")).read()
     oc = open(os.path.join(root, "oracle", "bmi_physics_oracle.c")).read()
     maxc = int(re.search(r"constexpr int MAXC = (\d+);", cu).group(1))
-    maxa = int(re.search(r"constexpr int MAXA = (\d+);", cu).group(1))
-    assert maxc == int(re.search(r"#define MAX_CONTACTS (\d+)", oc).group(1))
-    assert maxa == int(re.search(r"#define MAX_ARM_CONTACTS (\d+)", oc).group(1))
+    assert int(re.search(r"#define MAX_CONTACTS (\d+)", oc).group(1)) >= 4 * maxc
     # one solver lane per contact next to 9 joint lanes and 6 block-velocity lanes
     assert 16 + maxc <= 32 and 3 * maxc <= 32
     blob = np.fromfile(os.path.join(root, "rl_arm_under_sparse_reward_b200", "assets", "bmirobot_model.bin"), "<f4")

@@ -45,7 +45,8 @@ P = dict(magic=0, version=1, n_links=2, n_shapes=3, links_off=4, shapes_off=5, p
          push_hx=32, push_hy=33, push_hz=34, push_mass=35, push_mu=36,
          pick_hx=37, pick_hy=38, pick_hz=39, pick_mass=40, pick_mu=41,
          dist_threshold=42, joint_limit_force=43, block_margin=44, table_margin=45, ik_pos_at_com=46,
-         self_collision=47, warmstart=48)
+         self_collision=47, warmstart=48, hull_margin=49, self_split_diag=50, sweep_alternate=51, limits_first=52,
+         self_near=53, full_hulls=54)
 L = dict(parent=0, jpos=1, jrot=4, axis=13, lo=16, hi=17, damping=18, mass=19, com=20, inertia=23, shape=26, mu=27)
 
 
@@ -186,7 +187,10 @@ def main(k_verts=24):
     hdr[P["erp_joint"]], hdr[P["erp_contact"]], hdr[P["linear_slop"]] = 0.2, 0.08, 1e-5
     hdr[P["motor_kp"]], hdr[P["motor_kd"]], hdr[P["motor_force"]] = 0.03, 1.0, 500.0
     hdr[P["lin_damp"]], hdr[P["ang_damp"]] = 0.04, 0.04
-    hdr[P["ik_damping"]], hdr[P["ik_iters"]], hdr[P["ik_thresh"]], hdr[P["ik_max_angle"]] = 0.1, 20, 1e-4, np.pi / 4
+    # PyBullet's calculateInverseKinematics without jointDamping: joint_damping.resize(numDofs, 0.5) added to the diagonal
+    # of J^T J; 20 iterations, residual 1e-4, step capped at 45 degrees.  0.5 (not the 0.1 of round 1) is what the recorded
+    # episode 0 pins: first-step joint travel -0.0749 / -0.1554 rad recorded, -0.0777 / -0.1669 with 0.5, -0.137 / -0.223 with 0.1
+    hdr[P["ik_damping"]], hdr[P["ik_iters"]], hdr[P["ik_thresh"]], hdr[P["ik_max_angle"]] = 0.5, 20, 1e-4, np.pi / 4
     hdr[P["table_z"]], hdr[P["mu_table"]] = 0.175, 1.0
     hdr[P["contact_margin"]] = 0.002
     hdr[P["base_px"]:P["base_px"] + 3] = base
@@ -199,8 +203,32 @@ def main(k_verts=24):
     hdr[P["joint_limit_force"]] = 1000.0
     hdr[P["block_margin"]], hdr[P["table_margin"]] = 0.002, 0.0
     hdr[P["ik_pos_at_com"]] = 0.0
-    hdr[P["self_collision"]] = 0.0
+    # bmirobot.py:58 flags=9: URDF_USE_SELF_COLLISION (every link pair except child/parent).  Pinned on the recorded
+    # episode 0: the wrist holds at q6 = 0.1975 rad, the kink of the link6 x link8 penetration depth (0.1985 with these
+    # hulls); the elbow stalls at q4 = -0.7013 where link4 x link6 are 1 mm apart = inside the two 1 mm hull margins.
+    hdr[P["self_collision"]] = 1.0
+    hdr[P["hull_margin"]] = 0.001       # PyBullet URDF convex meshes: margin 0.001
+    hdr[P["self_split_diag"]] = 1.0     # Bullet's row diagonal for two links of one multibody has no cross term
+    hdr[P["sweep_alternate"]] = 1.0     # non-contact rows swept backwards on even iterations
+    hdr[P["limits_first"]] = 0.0
+    hdr[P["self_near"]] = 0.001         # separated pairs produce a (speculative) row below this distance; Bullet: 0.02 (identical
+                                        # trajectories measured for 0.001 .. 0.02: such rows only bind above 0.24 m/s approach speed)
+    hdr[P["full_hulls"]] = 0.0
     hdr[P["warmstart"]] = 0.0   # 0.85 (Bullet default) is implemented in the oracle only; the kernel does not warm-start yet
+
+    # full-resolution convex hulls of the ten right-arm collision meshes (self-collision; oracle narrow phase and the
+    # source of the kernel's baked pair tables): [n_hulls, per hull: link (-1 = right_link1, rigid with the base), friction,
+    # n_verts, 3 n_verts coordinates in the link frame]
+    hull_links = ["right_link1"] + [ji_child for ji_child in link_names]
+    hull_out = [float(len(hull_links))]
+    for ln in hull_links:
+        v = load_stl(os.path.join(MESH_DIR, mesh_of[ln]))
+        hv = v[ConvexHull(v).vertices]
+        fr = links[ln].find("contact/lateral_friction")
+        mu = float(fr.get("value")) if fr is not None else 0.5
+        hull_out += [float(link_index[ln]), mu, float(len(hv))] + hv.reshape(-1).tolist()
+        info[ln + "_hull"] = dict(verts=len(hv))
+    np.array(hull_out, dtype="<f4").tofile(os.path.join(OUT_DIR, "bmirobot_hulls.bin"))
 
     blob = np.concatenate([hdr, blob_links.reshape(-1), np.array(shapes, np.float64).reshape(-1), np.array(pool)])
     assert blob.shape[0] == int(hdr[P["total"]])
