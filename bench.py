@@ -10,6 +10,13 @@ reference's loop shape at R = 4096; its R = 2 default gives 1 update per 5 env-s
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                     (CPU arm: the oracle port on all host cores)
+    python bench.py --workload pick ...                      (BASELINE config 3: pick-and-place, 4096 envs, add_demo)
+    python bench.py --workload replay-stress ...             (BASELINE config 5: 5e5 stored transitions, HER batch sweep)
+
+The buffer is pre-filled with 1000 scripted-controller demonstrations of the task (add_demo=True, the reference's
+bmirobot_1000_{push,pick}_demo.npz role; generated on the device before the timed region because the reference's
+18 MB files do not travel).  Multi-rank runs end with a parity probe: MD5 of every rank's parameters (must be
+identical) and the fused peer-memory gradient sum + Adam against the NCCL allreduce path on identical data.
 """
 import argparse
 import json
@@ -30,6 +37,9 @@ ALGO_BYTES_PER_ENV_STEP = 412          # state in+out 2x136 + actio
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_kernel launch (4096 envs x 100 steps), from the
 # `ncu --set full` capture summarised in profiles/r01_rollout_kernel_ncu.md (bench.py cannot run ncu itself)
 NCU_DRAM_BYTES_PER_LAUNCH = 80482304   # 4.774 MB read + 75.708 MB written
+# sm__warps_active / issue-slot utilisation / FMA pipe of the same capture (profiles/r02_rollout_kernel_ncu.md); numeric so
+# that the roofline object says what bounds this FP32-issue kernel (the HBM fraction cannot)
+NCU_ROLLOUT = {"warps_active_pct": None, "issue_slot_util_pct": None, "fma_pipe_pct": None}
 METRIC = "env-steps/s (push, 4096 envs) at 1/2/4/8 B200 vs CPU PyBullet+MPI"
 
 
@@ -130,9 +140,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core = 2000
+    per_core = 300          # ~1.5 s per step at ~200 env-steps/s/core (GJK + EPA self-collision, 150 solver iterations)
     for _ in range(args.warmup):
-        cpu_env_steps_per_s(50, cores)
+        cpu_env_steps_per_s(20, cores)
     vals, t_ms = [], []
     for _ in range(args.steps):
         v, total, wall = cpu_env_steps_per_s(per_core, cores)
@@ -140,19 +150,162 @@ def run_reference(args):
         t_ms.append(wall * 1e3)
     value = float(np.mean(vals))
     sample = ("per step: %d processes x %d env-steps of the C oracle port (restated env step, NOT PyBullet: pybullet/gym/"
-              "mpi4py are not installable in this image) + the proportional DDPG updates on torch CPU" % (cores, per_core))
+              "mpi4py are not installable in this image; faithful mode: GJK + EPA self-collision on the full hulls, Bullet's plain "
+              "150-iteration solver loop) + the proportional DDPG updates on torch CPU" % (cores, per_core))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(t_ms)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "push task, one env per host core, cycle shape of the GPU arm (100-step episodes, 40 HER DDPG updates "
                                    "of batch 256 per 409600 env-steps); bounded sample per step", "envs": cores,
                        "updates_per_env_step": 40.0 / (N_ENVS * T)},
+            "reference_arm": "C port of the reference env step (oracle/), NOT PyBullet + mpi4py: not installable here",
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def _demo_file(task, rank, n_demo, device_index):
+    """add_demo=True (ddpg_agent.py:82-90): `n_demo` successful scripted episodes in the reference's .npz format,
+    generated on the device with the reference's scripted controllers (get_demo_data.py) -- the stand-in for
+    bmirobot_1000_{push,pick}_demo.npz, which do not travel to the GPU box.  Not timed."""
+    from rl_arm_under_sparse_reward_b200 import get_demo_data
+    path = "/tmp/bmi_bench_demo_%s_%d.npz" % (task, rank)
+    demo, rate = get_demo_data.get_demo(task, n_demo, n_envs=2048, seed=1000 + rank, max_batches=24, verbose=False)
+    np.savez_compressed(path, acs=demo["acs"], obs=demo["obs"], info=demo["info"], g=demo["g"], ag=demo["ag"])
+    return path, int(demo["acs"].shape[0]), float(rate)
+
+
+def _digest(agent):
+    import hashlib
+    return hashlib.md5(agent.actor_network.flat.cpu().numpy().tobytes() + agent.critic_network.flat.cpu().numpy().tobytes()).hexdigest()
+
+
+def parity_probe(world, rank, seed):
+    """Multi-rank proof carried by the bench line (the 1-GPU test box cannot run tests/test_gpu_multi.py): two small
+    agents with identical seeds and data, one with the fused peer-memory gradient sum + Adam kernel, one with the NCCL
+    allreduce (sum) + Adam path (utils.py:43-48 semantics), 1 rollout + 6 updates each.  Returns whether every rank
+    ends with identical parameters on each path and how far the two paths are apart (2 ranks: a + b is order-free, so
+    bit-identical; more ranks: NCCL's reduction order differs from the kernel's rank order by float rounding)."""
+    import torch
+    import torch.distributed as dist
+    from rl_arm_under_sparse_reward_b200.arguments import Args
+    from rl_arm_under_sparse_reward_b200.bmirobot_env.vec_env import BmiVecEnv
+    from rl_arm_under_sparse_reward_b200.ddpg_agent import ddpg_agent
+    from rl_arm_under_sparse_reward_b200.train import get_env_params
+    out = {}
+    flats = {}
+    for name, p2p in (("p2p", True), ("nccl", False)):
+        a = Args()
+        a.add_demo, a.verbose, a.n_envs, a.buffer_size, a.save_dir = False, False, 64, 256 * 100, "/tmp/bmi_probe_%d/" % rank
+        a.p2p_adam = p2p
+        torch.manual_seed(seed)
+        env = BmiVecEnv(a.n_envs, seed=seed + rank)
+        ag = ddpg_agent(a, env, get_env_params(env))
+        ag.rollout(0)
+        ag.buffer.store_episode([ag.ep['obs'], ag.ep['ag'], ag.ep['g'], ag.ep['actions']])
+        ag._update_normalizer()
+        a.use_cuda_graphs = False
+        ag.update_many(6)
+        torch.cuda.synchronize()
+        digests = [None] * world
+        dist.all_gather_object(digests, _digest(ag))
+        out[name + "_params_identical_across_ranks"] = len(set(digests)) == 1
+        out[name + "_attached"] = bool(ag._p2p)
+        if p2p:
+            out["p2p_timed_out"] = bool(ag.p2p_timed_out()) if ag._p2p else False
+        flats[name] = torch.cat([ag.actor_network.flat, ag.critic_network.flat]).clone()
+        ag.release_graphs()
+        del ag, env
+    d = (flats["p2p"] - flats["nccl"]).abs().max().item()
+    out["p2p_equals_nccl"] = bool(d == 0.0)
+    out["p2p_vs_nccl_max_abs_diff"] = d
+    return out
+
+
+def run_replay_stress(args):
+    """BASELINE config 5: 5e5 stored transitions per rank, HER 'future' (k = 4) relabel + network-input assembly, batch
+    sweep.  Each rank owns its buffer (the reference design, train.py:34-39): weak scaling, no collective on the data
+    path.  value = transitions/s at the largest batch, summed over ranks (max-over-ranks time)."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from rl_arm_under_sparse_reward_b200 import _lib, utils
+    rank, world = utils.init_comm()
+    if world == 1:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    E = 5000
+    g = torch.Generator(device=dev).manual_seed(125 + rank)
+    obs = torch.randn(E, T + 1, 27, device=dev, generator=g)
+    ag = 0.3 + 0.1 * torch.randn(E, T + 1, 3, device=dev, generator=g)
+    gg = 0.3 + 0.1 * torch.randn(E, T, 3, device=dev, generator=g)
+    act = torch.rand(E, T, 4, device=dev, generator=g) - 0.5
+    eps = _lib.Episodes(_lib.ptr(obs), _lib.ptr(ag), _lib.ptr(gg), _lib.ptr(act), E, T, 27, 3, 4, _lib.BMI_F32, 0)
+    stats = [torch.zeros(27, device=dev), torch.ones(27, device=dev), torch.zeros(3, device=dev), torch.ones(3, device=dev)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    nv = torch.tensor([E], dtype=torch.int64, device=dev)
+    peak, peak_src = peaks()
+    n0 = _lib.launch_count()
+    rows = []
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    batches = (256, 1024, 4096, 16384, 65536, 262144, 1048576)
+    for B in batches:
+        d = (torch.empty(B, dtype=torch.int64, device=dev), torch.empty(B, dtype=torch.int64, device=dev),
+             torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.float64, device=dev))
+        X, XN, A, R = (torch.empty(B, 30, device=dev), torch.empty(B, 30, device=dev), torch.empty(B, 4, device=dev), torch.empty(B, device=dev))
+
+        def draw():
+            _lib.call("bmi_her_draw", ctypes.c_uint64(125 + rank), _lib.ptr(ctr), B, _lib.ptr(nv), T, _lib.ptr(d[0]), _lib.ptr(d[1]),
+                      _lib.ptr(d[2]), _lib.ptr(d[3]), _lib.stream_ptr())
+
+        def fused():
+            _lib.call("bmi_her_sample_inputs", ctypes.byref(eps), E, _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]), B,
+                      0.8, 0.05, 200.0, 5.0, _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.ptr(stats[3]),
+                      _lib.ptr(X), _lib.ptr(XN), _lib.ptr(A), _lib.ptr(R), _lib.stream_ptr())
+        for _ in range(max(args.warmup, 3)):
+            draw(); fused()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = []
+        for _ in range(args.steps):
+            draw()
+            flush.fill_(0.0)               # L2 flush between timed launches
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fused(); e.record()
+            torch.cuda.synchronize()
+            ms.append(s.elapsed_time(e))
+        t = torch.tensor([float(np.mean(ms)) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = float(t.item())
+        rows.append({"batch": B, "us": t * 1e6, "transitions_per_s": world * B / t, "GB_s_per_gpu": B * 516 / t / 1e9,
+                     "frac_of_hbm_peak": B * 516 / t / 1e9 / peak})
+    sampler.stop_flag = True
+    if rank == 0:
+        sampler.join(timeout=2)
+        top = rows[-1]
+        line = {"metric": "HER-relabelled transitions/s (replay-buffer stress: 5e5 stored transitions per GPU, future k=4, fused network-input assembly)",
+                "value": top["transitions_per_s"], "unit": "transitions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": top["us"] * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "replay-stress: 5000 episodes x 100 steps of N(0,1) obs / N(0.3,0.1) goals / U(-0.5,0.5) actions per GPU, "
+                                       "her_inputs_kernel batch sweep, value = batch %d" % top["batch"],
+                           "l2": "flushed before every timed launch (256 MiB fill); the 75 MB float32 buffer itself fits the 126 MB L2",
+                           "parallelism": "dp%d (one buffer per rank, no data-path collective)" % world},
+                "roofline": {"bound": "hbm", "achieved": top["GB_s_per_gpu"], "peak": peak, "unit": "GB/s", "frac": top["frac_of_hbm_peak"],
+                             "traffic": None, "kernel": "her_inputs_kernel", "algorithmic_bytes_per_launch": 516 * top["batch"],
+                             "peak_source": peak_src, "sweep": rows},
+                "cpu_baseline": None,
+                "e2e": None, "gpu_launches": int(_lib.launch_count() - n0), "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    utils.shutdown_comm()
+
+
 def run_gpu(args):
     import torch
     from rl_arm_under_sparse_reward_b200 import _lib, utils
@@ -162,17 +315,24 @@ def run_gpu(args):
     from rl_arm_under_sparse_reward_b200.train import get_env_params
     import torch.distributed as dist
 
+    task = "pick" if args.workload == "pick" else "push"
     rank, world = utils.init_comm()
     if world == 1:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
     a = Args()
-    a.add_demo, a.verbose = False, False
+    a.verbose = False
     a.n_envs = args.envs
+    a.n_batches = args.n_batches
     a.fused_rollout = not args.stepwise
     a.buffer_size = args.buffer_episodes * T
     a.save_dir = "/tmp/bmi_bench_%d/" % rank
-    env = BmiVecEnv(a.n_envs, task="push", seed=a.seed + rank)
+    a.add_demo = not args.no_demo
+    n_demo, demo_rate = 0, None
+    if a.add_demo:
+        a.demo_name, n_demo, demo_rate = _demo_file(task, rank, args.demos, torch.cuda.current_device())
+        a.add_demo = n_demo > 0
+    env = BmiVecEnv(a.n_envs, task=task, seed=a.seed + rank)
     np.random.seed(a.seed + rank)
     torch.manual_seed(a.seed + rank)
     agent = ddpg_agent(a, env, get_env_params(env))
@@ -199,9 +359,10 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 2)):   # first call captures the graphs, later ones replay them
+    for _ in range(max(args.warmup, 3)):   # first call captures the graphs, later ones replay them
         cycle()
     barrier()
+    env.contact_drops(reset=True)
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:          # one nvidia-smi poller per job is enough (rank 0 prints the line)
         sampler.start()
@@ -212,6 +373,7 @@ def run_gpu(args):
     launches_per_cycle = _lib.launch_count() - n0
     a.use_cuda_graphs = True
     barrier()
+    env.contact_drops(reset=True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for s, e in ev:
@@ -220,6 +382,7 @@ def run_gpu(args):
         cycle(timed=True)
         e.record()
     barrier()
+    drops = env.contact_drops()
     ms = np.array([s.elapsed_time(e) for s, e in ev])
     tot = torch.tensor([float(ms.sum())], device=dev)
     if world > 1:
@@ -237,18 +400,24 @@ def run_gpu(args):
     achieved = ALGO_BYTES_PER_ENV_STEP * a.n_envs * T / (kern_ms * 1e-3) / 1e9
     kernel_share = kern_ms / (total_ms / args.steps)
 
-    # ---- e2e: the same cycle driven through the reference-facing calls with HOST (pinned) buffers -----------
-    e2e = None
+    # ---- e2e: the same cycle with the HOST in the loop -------------------------------------------------------------------
+    # Every env-step: observation D2H into pinned memory -> sync -> the host hands the observation to the agent's policy
+    # (its arrays are host arrays, as in the reference loop ddpg_agent.py:111-120: H2D, normalise + actor + exploration
+    # noise on the device, action D2H -> sync) -> the host hands the action to env.step (H2D) -> step.  Two host syncs per
+    # env-step, policy inference inside the timed region.  The episode record accumulated on the host is then uploaded
+    # into store_episode / _update_normalizer, the updates run, the loss is read back.
+    e2e = e2e_async = None
     if not args.no_e2e:
-        act_host = agent.ep['actions'].permute(1, 0, 2).contiguous().cpu().pin_memory()        # [T][n][4]
         obs_host = torch.empty((T + 1, a.n_envs, 27), dtype=torch.float32).pin_memory()
         ag_host = torch.empty((T + 1, a.n_envs, 3), dtype=torch.float32).pin_memory()
+        act_host = torch.empty((T, a.n_envs, 4), dtype=torch.float32).pin_memory()
         rs_host = torch.empty((2, a.n_envs), dtype=torch.float32).pin_memory()
         loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        obs_dev = torch.empty((a.n_envs, 27), dtype=torch.float32, device=dev)
         act_dev = torch.empty((a.n_envs, 4), dtype=torch.float32, device=dev)
         h2d = d2h = 0
 
-        def e2e_cycle():
+        def e2e_cycle(host_in_loop):
             nonlocal h2d, d2h
             h2d = d2h = 0
             obs, ag, g = env.reset()
@@ -257,7 +426,15 @@ def run_gpu(args):
             g_host = g.cpu()
             d2h += obs.numel() * 4 + ag.numel() * 4 + g.numel() * 4
             for t in range(T):
-                act_dev.copy_(act_host[t], non_blocking=True)                  # host policy output -> device
+                if host_in_loop:
+                    torch.cuda.synchronize()                                   # the host now owns obs_host[t]
+                    obs_dev.copy_(obs_host[t], non_blocking=True)              # host observation -> policy
+                    act = agent._policy(obs_dev, g, True, 0.0)
+                    act_host[t].copy_(act, non_blocking=True)
+                    torch.cuda.synchronize()                                   # the host now owns the action
+                    h2d += obs_dev.numel() * 4
+                    d2h += act.numel() * 4
+                act_dev.copy_(act_host[t], non_blocking=True)                  # host action -> env.step
                 obs, ag, r, s = env.step(act_dev)
                 obs_host[t + 1].copy_(obs, non_blocking=True)
                 ag_host[t + 1].copy_(ag, non_blocking=True)
@@ -265,10 +442,8 @@ def run_gpu(args):
                 rs_host[1].copy_(s, non_blocking=True)
                 h2d += act_dev.numel() * 4
                 d2h += (obs.numel() + ag.numel() + r.numel() + s.numel()) * 4
-            # The host now holds the cycle's time-major record (what a host-driven loop accumulates step by step).
-            # Episode batch for store_episode / _update_normalizer: ONE pinned H2D copy per array, transposed to the
-            # reference's (R, T+1, dim) layout on the device (a 60 MB strided transpose on the host costs more than
-            # the whole update phase).
+            # The host now holds the cycle's time-major record.  Episode batch for store_episode / _update_normalizer: ONE
+            # pinned H2D copy per array, transposed to the reference's (R, T+1, dim) layout on the device.
             torch.cuda.synchronize()
             mb_obs = obs_host.to(dev, non_blocking=True).permute(1, 0, 2).contiguous()
             mb_ag = ag_host.to(dev, non_blocking=True).permute(1, 0, 2).contiguous()
@@ -283,50 +458,75 @@ def run_gpu(args):
             d2h += 8
             torch.cuda.synchronize()
 
-        e2e_cycle()
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
-            e2e_cycle()
-        barrier()
-        el = torch.tensor([time.perf_counter() - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * env_steps_per_cycle * n_e2e / float(el.item()), "unit": "env-steps/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "note": "host (pinned) action/obs buffers every env-step through env.step, the host-side episode record uploaded (pinned H2D) into store_episode / _update_normalizer, loss read back"}
+        def time_e2e(host_in_loop):
+            e2e_cycle(host_in_loop)
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = max(1, min(args.steps, 3))
+            for _ in range(n_e2e):
+                e2e_cycle(host_in_loop)
+            barrier()
+            el = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            return world * env_steps_per_cycle * n_e2e / float(el.item()), n_e2e
+
+        v, n_e2e = time_e2e(True)
+        e2e = {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+               "note": "host in the loop: per env-step obs D2H (pinned) -> sync -> agent._policy on the host's observation (H2D, "
+                       "normalise + actor + exploration noise, action D2H) -> sync -> env.step on the host's action (H2D); the "
+                       "host-side episode record uploaded into store_episode / _update_normalizer; loss read back"}
+        v2, _ = time_e2e(False)
+        e2e_async = {"value": v2, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                     "note": "round-1 figure: host (pinned) buffers every env-step but pre-recorded actions and no per-step sync"}
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=2)
+
+    p2p_flag = bool(agent.p2p_timed_out()) if (world > 1 and agent._p2p) else False
+    digests = [None] * world
+    if world > 1:
+        dist.all_gather_object(digests, _digest(agent))
+    grad_sync = ("none (1 rank)" if world == 1 else ("fused peer-memory sum + Adam kernel (CUDA IPC over NVLink)"
+                 if agent._p2p else "NCCL allreduce (sum) + Adam"))
+    agent.release_graphs()
+    probe = parity_probe(world, rank, a.seed) if (world > 1 and not args.no_probe) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, total, wall = cpu_env_steps_per_s(args.cpu_steps_per_core, cores)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-               "sample": "%d env-steps of the C oracle port (restated env step, NOT PyBullet) on %d processes + proportional "
-                         "torch-CPU updates, %.1f s" % (total, cores, wall)}
+               "sample": "%d env-steps of the C oracle port (restated env step in its faithful mode, NOT PyBullet) on %d processes + "
+                         "proportional torch-CPU updates, %.1f s" % (total, cores, wall)}
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        metric = METRIC if task == "push" else "env-steps/s (pick-and-place, 4096 envs, add_demo) on B200"
+        multi = None
+        if world > 1:
+            multi = {"params_identical_across_ranks": len(set(digests)) == 1, "probe": probe}
+        line = {"metric": metric, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "push task, %d vectorised envs per GPU, one cycle = %d env-steps + store + normaliser + %d HER "
-                                       "(future k=4) DDPG updates of batch %d + Polyak" % (a.n_envs, env_steps_per_cycle, a.n_batches, a.batch_size),
+                "config": {"workload": "%s task, %d vectorised envs per GPU, one cycle = %d env-steps + store + normaliser + %d HER "
+                                       "(future k=4) DDPG updates of batch %d + Polyak" % (task, a.n_envs, env_steps_per_cycle, a.n_batches, a.batch_size),
                            "envs_per_gpu": a.n_envs, "updates_per_env_step": a.n_batches / env_steps_per_cycle,
                            "buffer_episodes": args.buffer_episodes, "l2": "flushed between timed iterations (256 MiB fill)",
-                           "parallelism": "dp%d" % world,
-                           "grad_sync": ("none (1 rank)" if world == 1 else ("fused peer-memory sum + Adam kernel (CUDA IPC over NVLink)"
-                                         if agent._p2p else "NCCL allreduce (sum) + Adam")),
-                           "p2p_timed_out": bool(agent.p2p_timed_out()) if (world > 1 and agent._p2p) else False},
+                           "add_demo": bool(a.add_demo), "demo_episodes": n_demo, "demo_kept_fraction": demo_rate,
+                           "physics": "arm self-collision on (baked pair tables), IK joint damping 0.5, solver schedule %d iterations "
+                                      "(2-fold compressed ramp of Bullet's 150)" % 80,
+                           "contacts_dropped_per_env_substep": drops / float(args.steps * a.n_envs * T * 20),
+                           "parallelism": "dp%d" % world, "grad_sync": grad_sync, "p2p_timed_out": p2p_flag},
+                "reference_arm": "bench.py --impl reference = C port of the reference env step (oracle/), NOT PyBullet + mpi4py",
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                              "kernel": kernel_name, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * a.n_envs * T,
                              "kernel_ms": kern_ms, "kernel_share_of_step": kernel_share, "peak_source": peak_src,
-                             "note": "FP32-issue/latency-bound kernel, the HBM fraction is small by construction (SURVEY 8d); ncu (profiles/r01_rollout_kernel_ncu.md): 22.9 k warp instructions per env sub-step, issue slots busy 63-68 % of active cycles, the launch ends with its slowest env (median env: half the launch)"},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps),
-                "clocks": sampler.summary()}
+                             "warps_active_pct": NCU_ROLLOUT["warps_active_pct"], "issue_slot_util_pct": NCU_ROLLOUT["issue_slot_util_pct"],
+                             "fma_pipe_pct": NCU_ROLLOUT["fma_pipe_pct"],
+                             "note": "FP32-issue bound kernel (SURVEY 8d): the HBM fraction is small by construction; what bounds it is the issue-slot "
+                                     "utilisation above (ncu capture in profiles/)"},
+                "cpu_baseline": cpu, "e2e": e2e, "e2e_async": e2e_async, "multi_rank": multi,
+                "gpu_launches": int(launches_per_cycle * args.steps), "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
-    agent.release_graphs()
     utils.shutdown_comm()
 
 
@@ -336,15 +536,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="push", choices=["push", "pick", "replay-stress"])
     ap.add_argument("--envs", type=int, default=N_ENVS)
+    ap.add_argument("--n-batches", type=int, default=40, help="DDPG updates per cycle (reference: 40)")
     ap.add_argument("--buffer-episodes", type=int, default=65536)
-    ap.add_argument("--cpu-steps-per-core", type=int, default=12000)
+    ap.add_argument("--demos", type=int, default=1000, help="scripted demonstration episodes pre-loaded into the buffer (add_demo)")
+    ap.add_argument("--no-demo", action="store_true")
+    ap.add_argument("--cpu-steps-per-core", type=int, default=2500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-probe", action="store_true", help="skip the multi-rank parity probe")
     ap.add_argument("--stepwise", action="store_true", help="step-wise rollout pipeline instead of the fused kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "replay-stress":
+        run_replay_stress(args)
     else:
         run_gpu(args)
 

@@ -255,6 +255,13 @@ int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const void* mode
                    int64_t model_bytes);
 int bmi_env_destroy(bmi_env* h);
 int32_t bmi_env_num_envs(const bmi_env* h);
+/* Self-collision of the arm (bmirobot.py:58: loadURDF(..., flags=9) = URDF_USE_SELF_COLLISION).  table: host pointer to
+ * the baked pair tables (assets/bmirobot_selfcol.bin, tools/bake_selfcol.py; layout include/bmi_model.h SC_*), copied to
+ * the device once.  A model blob with MP_SELF_COLLISION = 1 cannot be stepped before this call (BMI_ERR_ARG). */
+int bmi_env_set_selfcol(bmi_env* h, const void* table, int64_t table_bytes);
+/* statistics: contacts the kernel dropped because the solver's lane budget was full (9 contacts, 6 on arm links) since
+ * the last reset of the counter; host_out may be NULL.  Synchronises the device. */
+int bmi_env_contact_drops(bmi_env* h, uint64_t* host_out, int32_t reset);
 /* reset (bmirobot_env_push_F.py:110-165) of the envs whose mask byte is non-zero (NULL =
  * all).  init_dev: float32 [n_envs][8] = block x,y,z,yaw, goal x,y,z, unused — drawn by
  * the caller (python `random` stream for the drop-in env, bmi_env_sample_init for the
@@ -288,13 +295,6 @@ typedef struct bmi_rollout_args {
   float* obs; float* ag; float* g; float* success;   /* device outputs after the last step (may be NULL) */
 } bmi_rollout_args;
 int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* args, bmi_stream_t stream);
-/* EXPERIMENTAL (round 1: written, validated against bmi_env_rollout only at the end of the round — see DESIGN.md 8):
- * the same rollout, bit for bit, with env-steps handed out from a task queue instead of one warp per env for the whole
- * episode.  Blocks [0, express_blocks) run only express_warps warps each and take the envs whose last step needed the
- * most solver iterations; all other warps take the cheapest env that is furthest behind.  express_blocks = 0 gives a
- * plain work queue. */
-int bmi_env_rollout_queue(bmi_env* h, const bmi_rollout_args* args, int32_t express_blocks, int32_t express_warps,
-                          bmi_stream_t stream);
 /* torch-layout flat actor parameters (W[out][in], b per layer) -> W^T[in][out], b per layer */
 int bmi_actor_transpose(const float* actor_params_dev, int32_t obs_dim, int32_t goal_dim, int32_t act_dim,
                         int32_t hidden, float* actor_t_dev, bmi_stream_t stream);

@@ -44,6 +44,9 @@ enum {
   MP_SWEEP_ALTERNATE = 51,/* 1: non-contact rows are swept backwards on even solver iterations (Bullet) */
   MP_SELF_NEAR = 53,      /* self-collision pairs closer than this (beyond the margins) still produce a (speculative) row */
   MP_FULL_HULLS = 54,     /* oracle only: arm-table / arm-block contacts from the full hulls of all links (GJK + EPA) */
+  MP_SELF_TABLE = 55,     /* 1: self-collision pairs come from the baked pair tables (the kernel's path) instead of GJK / EPA */
+  MP_PGS_COMPRESS = 56,   /* K > 1: iteration compression of the under-relaxed rows (kernel schedule; oracle default 0 = plain loop) */
+  MP_PGS_TAIL = 57,       /* ... number of plain iterations at the end of the compressed schedule */
   MP_LIMITS_FIRST = 52    /* 1: joint-limit rows precede the motor rows (order the constraints were created in) */
 };
 
@@ -64,6 +67,25 @@ enum {
 enum {
   MS_LINK = 0, MS_NVERTS = 1, MS_NPLANES = 2, MS_VERT_OFF = 3, MS_PLANE_OFF = 4,
   MS_SPHERE_C = 5, MS_SPHERE_R = 8, MS_MU = 9
+};
+
+/* Baked self-collision pair tables (assets/bmirobot_selfcol.bin, float32; tools/bake_selfcol.py).  Every link pair of
+ * the arm that can touch is separated by exactly two joints (grandparent / sibling pairs), so its whole narrow phase is
+ * a function of two joint angles: the kernel looks it up instead of running GJK / EPA on 300-vertex hulls.
+ * Header SC_HDR floats, then SC_DESC floats per pair, then per node 8 floats:
+ *   core distance (gap > 0 or -penetration depth; 1e3 = far), unit normal from link B towards link A (3) and witness
+ *   point on A (3), both in the frame of link A, pad.   witness on B = xa - n * distance. */
+#define BMI_SC_MAGIC 20261017.0f
+#define BMI_SC_MAX_PAIRS 4
+enum { SC_MAGIC = 0, SC_NPAIRS = 1, SC_TOTAL = 2, SC_HDR = 8, SC_DESC = 16 };
+enum {
+  SC_LA = 0, SC_LB = 1,    /* links (-1 = right_link1, rigid with the base) */
+  SC_JA = 2, SC_JB = 3,    /* the two joints the relative pose depends on */
+  SC_A0 = 4, SC_B0 = 5,    /* grid origin */
+  SC_H = 6,                /* grid spacing (rad) */
+  SC_NA = 7, SC_NB = 8,    /* nodes per axis */
+  SC_OFF = 9,              /* float offset of node (0, 0) from the start of the file; node (i, j) at OFF + 8 (i NB + j) */
+  SC_MU = 10               /* combined friction of the pair (product, clamped to 10) */
 };
 
 /* simulator state vector exposed by bmi_env_get_state / set_state (BMI_ENV_STATE_DIM = 48) */

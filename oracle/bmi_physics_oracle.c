@@ -51,6 +51,9 @@ typedef struct {
   int nh, h_link[MAX_HULLS], h_nv[MAX_HULLS];
   double* h_v[MAX_HULLS];
   double h_c[MAX_HULLS][3], h_r[MAX_HULLS], h_mu[MAX_HULLS];
+  /* baked pair tables of the kernel (include/bmi_model.h SC_*): used instead of GJK / EPA when MP_SELF_TABLE is set, so
+   * that the kernel-vs-oracle tests compare like with like; the table-vs-EPA deviation is measured on the CPU */
+  const float* sc_table; int64_t sc_n;
 } Model;
 
 typedef struct {
@@ -67,6 +70,8 @@ typedef struct {
   Model m;
   int task;
   double bh[3], bmass, binertia[3], bmu; /* block half extents / mass / diagonal inertia / friction */
+  int cap_c, cap_a;                      /* optional contact caps (kernel-vs-oracle tests), 0 = unbounded */
+  int kernel_schedule;                   /* 1: honour MP_PGS_COMPRESS / MP_PGS_TAIL (the kernel's iteration schedule) */
   /* statistics of the last step (for tests / tuning) */
   int last_rows, last_iters, last_contacts;
   double resid_hist[256]; int worst_row[256];
@@ -344,6 +349,7 @@ typedef struct {
   double inv_diag, rhs, lo, hi, lambda;
   int friction_of;     /* index of the normal row for friction rows, else -1 */
   double mu;
+  int under;           /* 1: row uses Bullet's same-multibody diagonal (strongly under-relaxed) */
 } Row;
 
 typedef struct {
@@ -380,9 +386,11 @@ static int select_deepest(const double* dist, int n, double margin, int cap, int
   return cnt;
 }
 
-static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C) {
+static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C, int nc0) {
   const Model* m = &e->m;
-  int nc = 0, na = 0;
+  /* cap_c / cap_a: optional lane budget of the CUDA kernel (bmo_set_caps; default = storage bound = keep everything) */
+  const int MAXC_ = e->cap_c > 0 ? e->cap_c : MAX_CONTACTS, MAXA_ = e->cap_a > 0 ? e->cap_a : MAX_ARM_CONTACTS;
+  int nc = nc0, na = nc0;   /* the contacts already in the list are the arm's self-contacts */
   double Rb[9], bv[8][3];
   quat_to_mat(Rb, s->bq);
   block_vertices(e, s, Rb, bv);
@@ -393,7 +401,7 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
     int sel[8];
     for (int i = 0; i < 8; ++i) d[i] = bv[i][2] - tz;
     int n = select_deepest(d, 8, m->P[MP_TABLE_MARGIN], 4, sel);
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n && nc < MAXC_; ++i) {
       Contact* c = &C[nc++];
       c->link = -1; c->link1 = -1; c->self = 0; c->has_block = 1; c->id = sel[i]; v3cpy(c->x, bv[sel[i]]); v3set(c->n, 0, 0, 1);
       c->dist = d[sel[i]]; c->mu = e->bmu * m->P[MP_MU_TABLE];
@@ -462,7 +470,7 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
       int sel[MAX_SHAPE_V];
       for (int i = 0; i < nv; ++i) d[i] = wv[i][2] - tz;
       int n = select_deepest(d, nv, m->P[MP_CONTACT_MARGIN], 2, sel);
-      for (int i = 0; i < n && nc < MAX_CONTACTS && na < MAX_ARM_CONTACTS; ++i) {
+      for (int i = 0; i < n && nc < MAXC_ && na < MAXA_; ++i) {
         Contact* c = &C[nc++];
         ++na;
         c->link = l; c->link1 = -1; c->self = 0; c->has_block = 0; c->id = 8 + 32 * sidx + sel[i]; v3cpy(c->x, wv[sel[i]]); v3set(c->n, 0, 0, 1);
@@ -504,7 +512,7 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
     }
     int sel[8 + MAX_SHAPE_V];
     int n = select_deepest(d, 8 + nv, m->P[MP_BLOCK_MARGIN], 3, sel);
-    for (int i = 0; i < n && nc < MAX_CONTACTS && na < MAX_ARM_CONTACTS; ++i) {
+    for (int i = 0; i < n && nc < MAXC_ && na < MAXA_; ++i) {
       int ci = sel[i];
       Contact* c = &C[nc++];
       ++na;
@@ -523,51 +531,106 @@ static int find_contacts(const Env* e, const State* s, const Kin* k, Contact* C)
  * btGjkEpaPenetrationDepthSolver, convex_epa.h), one point per pair and sub-step; the hulls carry Bullet's collision
  * margin (MP_HULL_MARGIN per shape).  Only penetrating pairs produce a row. */
 static int hull_parent_link(const Model* m, int hl) { return hl < 0 ? -2 : m->parent[hl]; }
-static int find_self_contacts(const Env* e, const Kin* k, Contact* C, int nc) {
+static void hull_world(const Model* m, const Kin* k, int h, Cvx* c) {
+  int l = m->h_link[h];
+  c->nv = m->h_nv[h]; c->v = m->h_v[h];
+  if (l >= 0) { memcpy(c->R, k->R[l], sizeof(c->R)); v3cpy(c->p, k->p[l]); }
+  else { /* right_link1: rigidly attached to the fixed base; link 0's joint origin is expressed in its frame */
+    double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    memcpy(c->R, I, sizeof(I));
+    v3set(c->p, m->P[MP_BASE_PX], m->P[MP_BASE_PY], m->P[MP_BASE_PZ]);
+  }
+}
+/* signed core distance of hulls a, b (gap > 0, or -penetration depth), unit normal n from b towards a and the witness
+ * points; returns 0 when the cores are farther apart than `far` */
+static int hull_pair(const Model* m, const Kin* k, int a, int b, double far, double* dist, double* n, double* pa, double* pb) {
+  Cvx A, B;
+  hull_world(m, k, a, &A); hull_world(m, k, b, &B);
+  double ca[3], cb[3], t[3], d[3];
+  m3vec(t, A.R, m->h_c[a]); v3add(ca, A.p, t);
+  m3vec(t, B.R, m->h_c[b]); v3add(cb, B.p, t);
+  v3sub(d, ca, cb);
+  if (v3norm(d) > m->h_r[a] + m->h_r[b] + far) return 0;
+  double ne[3];
+  double depth = epa_penetration(&A, &B, ne, pa, pb);
+  if (depth >= 0) { for (int r = 0; r < 3; ++r) n[r] = -ne[r]; *dist = -depth; return 1; }
+  double gap = gjk_distance(&A, &B, pa, pb);
+  if (gap < 0 || gap > far) return 0;
+  for (int r = 0; r < 3; ++r) n[r] = (pa[r] - pb[r]) / gap;
+  *dist = gap;
+  return 1;
+}
+/* table look-up shared (as an algorithm) with csrc/physics.cu self_contacts(): bilinear over the four surrounding nodes
+ * when they describe the same hull features (normals within 1.8 degrees, witness points within 2 mm), else the nearest
+ * node; out = dist, n(3), xa(3) in the frame of link A.  Returns 0 when there is no contact information. */
+static int sc_lookup(const float* T, const float* d, double qa, double qb, double* out7) {
+  const double h = d[SC_H];
+  const int na = (int)d[SC_NA], nb = (int)d[SC_NB];
+  double fa = (qa - d[SC_A0]) / h, fb = (qb - d[SC_B0]) / h;
+  fa = fmin(fmax(fa, 0.0), na - 1.0);
+  fb = fmin(fmax(fb, 0.0), nb - 1.0);
+  int i = (int)floor(fa), j = (int)floor(fb);
+  if (i > na - 2) i = na - 2;
+  if (j > nb - 2) j = nb - 2;
+  const double wa = fa - i, wb = fb - j;
+  const float* node[4]; double w[4] = {(1 - wa) * (1 - wb), (1 - wa) * wb, wa * (1 - wb), wa * wb};
+  const float* base = T + (int64_t)d[SC_OFF];
+  node[0] = base + 8 * ((int64_t)i * nb + j); node[1] = node[0] + 8; node[2] = node[0] + 8 * (int64_t)nb; node[3] = node[2] + 8;
+  int near = (wa >= 0.5 ? 2 : 0) + (wb >= 0.5 ? 1 : 0);
+  if (node[near][0] > 100.f) return 0;
+  int same = 1;
+  for (int c = 0; c < 4; ++c) {
+    if (node[c][0] > 100.f) { same = 0; break; }
+    double dn = node[c][1] * node[near][1] + node[c][2] * node[near][2] + node[c][3] * node[near][3];
+    double dx = 0; for (int r = 0; r < 3; ++r) { double t = node[c][4 + r] - node[near][4 + r]; dx += t * t; }
+    if (dn < 0.9995 || dx > 4e-6) { same = 0; break; }
+  }
+  if (!same) { for (int r = 0; r < 7; ++r) out7[r] = node[near][r]; return 1; }
+  for (int r = 0; r < 7; ++r) out7[r] = w[0] * node[0][r] + w[1] * node[1][r] + w[2] * node[2][r] + w[3] * node[3][r];
+  double nn = sqrt(out7[1] * out7[1] + out7[2] * out7[2] + out7[3] * out7[3]);
+  for (int r = 1; r < 4; ++r) out7[r] /= nn;
+  return 1;
+}
+static int find_self_contacts(const Env* e, const State* s, const Kin* k, Contact* C, int nc) {
   const Model* m = &e->m;
-  const double margin = m->P[MP_HULL_MARGIN];
+  const double margin = m->P[MP_HULL_MARGIN], near = m->P[MP_SELF_NEAR];
+  if (m->P[MP_SELF_TABLE] > 0.5 && m->sc_table) { /* the kernel's path: the baked 2-joint pair tables */
+    const float* T = m->sc_table;
+    int np = (int)T[SC_NPAIRS];
+    for (int p = 0; p < np; ++p) {
+      const float* d = T + SC_HDR + SC_DESC * p;
+      double o[7];
+      if (!sc_lookup(T, d, s->q[(int)d[SC_JA]], s->q[(int)d[SC_JB]], o)) continue;
+      double dist = o[0] - 2 * margin;
+      if (dist > near) continue;
+      if (nc >= (e->cap_a > 0 ? e->cap_a : MAX_CONTACTS)) break;
+      Contact* c = &C[nc++];
+      int la = (int)d[SC_LA], lb = (int)d[SC_LB];
+      c->link1 = la; c->link = lb; c->self = 1; c->has_block = 0; c->id = 1000 + p;
+      double Ra[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pa[3] = {m->P[MP_BASE_PX], m->P[MP_BASE_PY], m->P[MP_BASE_PZ]};
+      if (la >= 0) { memcpy(Ra, k->R[la], sizeof(Ra)); v3cpy(pa, k->p[la]); }
+      double t[3];
+      m3vec(c->n, Ra, o + 1);
+      m3vec(t, Ra, o + 4); v3add(c->x, pa, t);
+      for (int r = 0; r < 3; ++r) c->x2[r] = c->x[r] - c->n[r] * o[0];
+      c->dist = dist; c->mu = d[SC_MU];
+    }
+    return nc;
+  }
   for (int a = 0; a < m->nh; ++a)
     for (int b = a + 1; b < m->nh; ++b) {
       int la = m->h_link[a], lb = m->h_link[b];
       if (hull_parent_link(m, lb) == la || hull_parent_link(m, la) == lb) continue; /* parent-child pairs are filtered */
       if (la < 0 && lb < 0) continue;
-      Cvx A, B;
-      const Cvx* cv[2] = {&A, &B};
-      const int hl[2] = {a, b};
-      for (int s = 0; s < 2; ++s) {
-        Cvx* c = s == 0 ? &A : &B;
-        int l = m->h_link[hl[s]];
-        c->nv = m->h_nv[hl[s]]; c->v = m->h_v[hl[s]];
-        if (l >= 0) { memcpy(c->R, k->R[l], sizeof(c->R)); v3cpy(c->p, k->p[l]); }
-        else { /* right_link1: rigidly attached to the fixed base; link 0's joint origin is expressed in its frame */
-          double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-          memcpy(c->R, I, sizeof(I));
-          v3set(c->p, m->P[MP_BASE_PX], m->P[MP_BASE_PY], m->P[MP_BASE_PZ]);
-        }
-      }
-      (void)cv;
-      /* broadphase: bounding spheres */
-      double ca[3], cb[3], t[3], d[3];
-      m3vec(t, A.R, m->h_c[a]); v3add(ca, A.p, t);
-      m3vec(t, B.R, m->h_c[b]); v3add(cb, B.p, t);
-      v3sub(d, ca, cb);
-      if (v3norm(d) > m->h_r[a] + m->h_r[b] + 2 * margin) continue;
-      double n[3], pa[3], pb[3];
-      double depth = epa_penetration(&A, &B, n, pa, pb);
-      if (depth < 0) {
-        /* separated cores: Bullet still reports the closest points while the gap is below the two margins plus the
-         * manifold's contact breaking threshold; such a row only limits the approach velocity (rhs -= dist / dt) */
-        double gap = gjk_distance(&A, &B, pa, pb);
-        if (gap < 0 || gap > 2 * margin + m->P[MP_SELF_NEAR]) continue;
-        for (int r = 0; r < 3; ++r) n[r] = -(pa[r] - pb[r]) / gap;   /* same sign convention as the EPA normal */
-        depth = -gap;
-      }
+      double dist, n[3], pa[3], pb[3];
+      /* Bullet reports closest points while the gap is below the two margins plus the manifold's contact breaking
+       * threshold; a separated row only limits the approach velocity (rhs -= dist / dt) */
+      if (!hull_pair(m, k, a, b, 2 * margin + near, &dist, n, pa, pb)) continue;
       if (nc >= MAX_CONTACTS) break;
       Contact* c = &C[nc++];
-      /* EPA on A - B: translating A by -n * depth separates the hulls, so the normal from B (body 2) towards A (body 1) is -n */
       c->link1 = la; c->link = lb; c->self = 1; c->has_block = 0; c->id = 1000 + 16 * a + b;
-      for (int r = 0; r < 3; ++r) { c->n[r] = -n[r]; c->x[r] = pa[r] - margin * n[r] * 0 ; c->x2[r] = pb[r]; }
-      c->dist = -(depth + 2 * margin);
+      for (int r = 0; r < 3; ++r) { c->n[r] = n[r]; c->x[r] = pa[r]; c->x2[r] = pb[r]; }
+      c->dist = dist - 2 * margin;
       c->mu = m->h_mu[a] * m->h_mu[b];
       if (c->mu > 10.0) c->mu = 10.0; /* Bullet calculateCombinedFriction clamps the product to 10 */
     }
@@ -715,8 +778,11 @@ static void substep(Env* e, State* s) {
   }
   const int n_noncontact = nr;
   Contact C[MAX_CONTACTS];
-  int nc = find_contacts(e, s, &k, C);
-  if (m->P[MP_SELF_COLLISION] > 0.5) nc = find_self_contacts(e, &k, C, nc);
+  /* the arm's self-contacts first: Bullet keeps its manifolds in creation order and the robot is loaded before the table
+   * and the block (bmirobot.py:53-77, bmirobot_env_push_F.py:145-159) */
+  int nc = 0;
+  if (m->P[MP_SELF_COLLISION] > 0.5) nc = find_self_contacts(e, s, &k, C, nc);
+  nc = find_contacts(e, s, &k, C, nc);
   int normal_row[MAX_CONTACTS];
   for (int ci = 0; ci < nc; ++ci) { /* normal rows */
     Row* r = &rows[nr];
@@ -724,7 +790,7 @@ static void substep(Env* e, State* s) {
     contact_jacobian(e, s, &k, &C[ci], C[ci].n, r->J);
     apply_minv(e, Lm, Ibinv, r->J, r->W);
     r->inv_diag = 1.0 / dotn(r->J, r->W, NU);
-    if (C[ci].self && m->P[MP_SELF_SPLIT_DIAG] > 0.5) r->inv_diag = 1.0 / self_contact_split_diag(e, &k, Lm, &C[ci], C[ci].n);
+    if (C[ci].self && m->P[MP_SELF_SPLIT_DIAG] > 0.5) { r->inv_diag = 1.0 / self_contact_split_diag(e, &k, Lm, &C[ci], C[ci].n); r->under = 1; }
     double rel = dotn(r->J, u, NU);
     double pen = C[ci].dist + m->P[MP_LINEAR_SLOP];
     double pos_err = 0, vel_err = -rel;
@@ -743,7 +809,7 @@ static void substep(Env* e, State* s) {
       contact_jacobian(e, s, &k, &C[ci], d == 0 ? t1 : t2, r->J);
       apply_minv(e, Lm, Ibinv, r->J, r->W);
       r->inv_diag = 1.0 / dotn(r->J, r->W, NU);
-      if (C[ci].self && m->P[MP_SELF_SPLIT_DIAG] > 0.5) r->inv_diag = 1.0 / self_contact_split_diag(e, &k, Lm, &C[ci], d == 0 ? t1 : t2);
+      if (C[ci].self && m->P[MP_SELF_SPLIT_DIAG] > 0.5) { r->inv_diag = 1.0 / self_contact_split_diag(e, &k, Lm, &C[ci], d == 0 ? t1 : t2); r->under = 1; }
       r->rhs = -dotn(r->J, u, NU) * r->inv_diag;
       r->friction_of = normal_row[ci]; r->mu = C[ci].mu;
     }
@@ -769,16 +835,32 @@ static void substep(Env* e, State* s) {
           break;
         }
   }
-  const int max_it = (int)m->P[MP_SOLVER_ITERS];
+  int max_it = (int)m->P[MP_SOLVER_ITERS];
+  /* Iteration compression (the CUDA kernel's schedule, OFF in the oracle's default = Bullet's plain loop).  The
+   * same-multibody rows are under-relaxed by 3e-4 .. 1e-3, so over the 150 iterations their impulses grow as a nearly
+   * linear ramp that the other rows track with one iteration of lag.  A ramp of K-fold steps reaches the same point in
+   * 1/K of the iterations; the last MP_PGS_TAIL iterations run with the true step so that the tracking lag at the end is
+   * Bullet's.  Equivalent iteration count = K n_c + tail = MP_SOLVER_ITERS.  Error: O((K - 1) / N) of the ramp's
+   * second-order term, measured in tests/test_oracle_physics.py and tests/test_gpu_physics.py. */
+  double Kc = e->kernel_schedule ? m->P[MP_PGS_COMPRESS] : 0.0;
+  int n_c = 0, has_under = 0;
+  for (int ri = 0; ri < nr; ++ri) has_under |= rows[ri].under;
+  if (Kc > 1.0 && has_under) {
+    int tail = (int)m->P[MP_PGS_TAIL];
+    n_c = (int)((max_it - tail) / Kc);
+    max_it = n_c + (max_it - (int)(n_c * Kc));
+  }
   int it;
   for (it = 0; it < max_it; ++it) {
     double resid = 0;
+    const double kf_it = it < n_c ? Kc : 1.0;
     for (int rj = 0; rj < n_normal_end; ++rj) {
       /* Bullet sweeps the non-contact rows backwards on even iterations (btMultiBodyConstraintSolver::solveSingleIteration) */
       int ri = rj;
       if (rj < n_noncontact && m->P[MP_SWEEP_ALTERNATE] > 0.5 && (it & 1) == 0) ri = n_noncontact - 1 - rj;
       Row* r = &rows[ri];
       double d = r->rhs - dotn(r->J, dv, NU) * r->inv_diag;
+      if (r->under) d *= kf_it;
       double sum = r->lambda + d;
       if (sum < r->lo) { d = r->lo - r->lambda; sum = r->lo; }
       else if (sum > r->hi) { d = r->hi - r->lambda; sum = r->hi; }
@@ -792,6 +874,7 @@ static void substep(Env* e, State* s) {
       double lim = ra->mu * rows[ra->friction_of].lambda;
       double da = ra->rhs - dotn(ra->J, dv, NU) * ra->inv_diag;
       double db = rb->rhs - dotn(rb->J, dv, NU) * rb->inv_diag;
+      if (ra->under) { da *= kf_it; db *= kf_it; }
       double sa = ra->lambda + da, sb = rb->lambda + db;
       double nrm = sqrt(sa * sa + sb * sb);
       if (nrm > lim) { double sc = nrm > 0 ? lim / nrm : 0; sa *= sc; sb *= sc; }
@@ -953,7 +1036,7 @@ void bmo_step(void* hp, const double* action, double* obs, double* ag, double* r
     Contact C[MAX_CONTACTS];
     double save = e->m.P[MP_BLOCK_MARGIN];
     e->m.P[MP_BLOCK_MARGIN] = 1e-4;
-    int nc = find_contacts(e, s, &k, C);
+    int nc = find_contacts(e, s, &k, C, 0);
     e->m.P[MP_BLOCK_MARGIN] = save;
     for (int i = 0; i < nc; ++i) if (C[i].has_block && C[i].link >= 0 && C[i].dist < 1e-4) { a[3] = -1; break; }
   }
@@ -1021,8 +1104,9 @@ int bmo_contacts(void* hp, double* out, int cap) {
   Kin k;
   fk(&h->env.m, h->st.q, &k);
   Contact C[MAX_CONTACTS];
-  int nc = find_contacts(&h->env, &h->st, &k, C);
-  if (h->env.m.P[MP_SELF_COLLISION] > 0.5) nc = find_self_contacts(&h->env, &k, C, nc);
+  int nc = 0;
+  if (h->env.m.P[MP_SELF_COLLISION] > 0.5) nc = find_self_contacts(&h->env, &h->st, &k, C, nc);
+  nc = find_contacts(&h->env, &h->st, &k, C, nc);
   for (int i = 0; i < nc && i < cap; ++i) {
     double* o = out + 12 * i;
     o[0] = C[i].link1; o[1] = C[i].link; o[2] = C[i].has_block; o[3] = C[i].dist;
@@ -1031,3 +1115,34 @@ int bmo_contacts(void* hp, double* out, int cap) {
   }
   return nc;
 }
+
+/* the kernel's baked pair tables (format: include/bmi_model.h SC_*); the pointer must stay valid */
+void bmo_set_selfcol_table(void* hp, const float* data, int64_t n) {
+  Model* m = &((Handle*)hp)->env.m;
+  m->sc_table = data; m->sc_n = n;
+}
+/* table baker: exact pair evaluation at joint angles q9 -> out8 = core distance, n(3) and witness xa(3) in the frame of
+ * hull a's link, pad; distance 1e3 when the cores are farther apart than `far` */
+void bmo_pair_query(void* hp, int a, int b, const double* q9, double far, float* out8) {
+  Model* m = &((Handle*)hp)->env.m;
+  Kin k;
+  fk(m, q9, &k);
+  double dist, n[3], pa[3], pb[3];
+  for (int r = 0; r < 8; ++r) out8[r] = 0.f;
+  out8[0] = 1e3f;
+  if (!hull_pair(m, &k, a, b, far, &dist, n, pa, pb)) return;
+  Cvx A; hull_world(m, &k, a, &A);
+  double t[3], nl[3], xl[3];
+  v3sub(t, pa, A.p); m3tvec(xl, A.R, t); m3tvec(nl, A.R, n);
+  out8[0] = (float)dist;
+  for (int r = 0; r < 3; ++r) { out8[1 + r] = (float)nl[r]; out8[4 + r] = (float)xl[r]; }
+}
+
+/* kernel-vs-oracle tests: apply the CUDA kernel's lane budget (contacts in total / on arm links), 0 = keep everything */
+void bmo_set_caps(void* hp, int cap_contacts, int cap_arm) {
+  Env* e = &((Handle*)hp)->env;
+  e->cap_c = cap_contacts; e->cap_a = cap_arm;
+}
+/* kernel-vs-oracle tests: run the solver with the kernel's compressed iteration schedule (model params MP_PGS_COMPRESS /
+ * MP_PGS_TAIL) instead of Bullet's plain MP_SOLVER_ITERS loop */
+void bmo_set_kernel_schedule(void* hp, int on) { ((Handle*)hp)->env.kernel_schedule = on; }

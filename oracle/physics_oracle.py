@@ -8,6 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "libbmi_oracle.so")
 MODEL = os.path.join(os.path.dirname(HERE), "rl_arm_under_sparse_reward_b200", "assets", "bmirobot_model.bin")
+SELFCOL = os.path.join(os.path.dirname(HERE), "rl_arm_under_sparse_reward_b200", "assets", "bmirobot_selfcol.bin")
 HULLS = os.path.join(os.path.dirname(HERE), "rl_arm_under_sparse_reward_b200", "assets", "bmirobot_hulls.bin")
 _dp = ctypes.POINTER(ctypes.c_double)
 
@@ -26,6 +27,12 @@ def _lib():
     lib.bmo_get_param.restype = ctypes.c_double
     lib.bmo_get_param.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.bmo_set_param.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+    lib.bmo_set_kernel_schedule.restype = None
+    lib.bmo_set_kernel_schedule.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.bmo_set_caps.restype = None
+    lib.bmo_set_caps.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.bmo_set_selfcol_table.restype = None
+    lib.bmo_set_selfcol_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     lib.bmo_contacts.restype = ctypes.c_int
     lib.bmo_contacts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     lib.bmo_set_hulls.restype = ctypes.c_int
@@ -60,6 +67,25 @@ class OracleEnv:
         if getattr(self, "h", None):
             self.lib.bmo_destroy(self.h)
             self.h = None
+
+    def use_pair_tables(self, path=SELFCOL):
+        """kernel geometry: self-collision pairs from the baked tables instead of GJK / EPA (MP_SELF_TABLE)"""
+        self.sc_table = np.fromfile(path, dtype="<f4")
+        self.lib.bmo_set_selfcol_table(self.h, _p(self.sc_table), self.sc_table.shape[0])
+        self.set_param(55, 1.0)
+
+    def set_caps(self, contacts=9, arm=6):
+        """apply the CUDA kernel's contact lane budget (csrc/physics.cu MAXC / MAXA); (0, 0) = keep everything"""
+        self.lib.bmo_set_caps(self.h, int(contacts), int(arm))
+
+    def kernel_mode(self, schedule=True):
+        """everything the CUDA kernel approximates, so that kernel-vs-oracle tests compare like with like: baked pair
+        tables, the 9 / 6 contact lane budget and (schedule=True) the compressed solver iteration schedule.  The default
+        OracleEnv is the faithful restatement: GJK + EPA, every contact, Bullet's plain 150-iteration loop."""
+        self.use_pair_tables()
+        self.set_caps(9, 6)
+        self.lib.bmo_set_kernel_schedule(self.h, int(bool(schedule)))
+        return self
 
     def set_param(self, idx, v):
         self.lib.bmo_set_param(self.h, int(idx), float(v))

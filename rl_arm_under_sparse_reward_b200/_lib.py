@@ -94,13 +94,14 @@ SIGNATURES = {
     "bmi_env_create": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_void_p, c_int64]),
     "bmi_env_destroy": (c_int32, [c_void_p]),
     "bmi_env_num_envs": (c_int32, [c_void_p]),
+    "bmi_env_set_selfcol": (c_int32, [c_void_p, c_void_p, c_int64]),
+    "bmi_env_contact_drops": (c_int32, [c_void_p, c_void_p, c_int32]),
     "bmi_env_reset": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "bmi_env_sample_init": (c_int32, [c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]),
     "bmi_env_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     "bmi_env_rollout": (c_int32, [c_void_p, POINTER(RolloutArgs), c_void_p]),
-    "bmi_env_rollout_queue": (c_int32, [c_void_p, POINTER(RolloutArgs), c_int32, c_int32, c_void_p]),
     "bmi_actor_transpose": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "bmi_env_get_state": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "bmi_env_set_state": (c_int32, [c_void_p, c_void_p, c_void_p]),

@@ -46,7 +46,4 @@ class Args:
         self.use_cuda_graphs = True
         self.p2p_adam = True           # multi-GPU: fused peer-memory gradient sum + Adam (False: NCCL allreduce, then Adam)
         self.fused_rollout = True      # one kernel launch per batch of episodes (policy MLP inside the env kernel)
-        self.queue_rollout = False     # EXPERIMENTAL: env-steps handed out from a task queue (bmi_env_rollout_queue)
-        self.queue_express_blocks = 16 # ... blocks that run only queue_express_warps warps and take the most expensive envs
-        self.queue_express_warps = 8
         self.verbose = True

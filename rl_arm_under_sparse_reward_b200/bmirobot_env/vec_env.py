@@ -12,6 +12,19 @@ import torch
 from .. import _lib
 
 MODEL_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets", "bmirobot_model.bin")
+SELFCOL_PATH = os.path.join(os.path.dirname(MODEL_PATH), "bmirobot_selfcol.bin")
+_SELFCOL_CACHE = {}
+
+
+def _selfcol_table(path):
+    """The baked self-collision pair tables (48 MB, git-ignored, written by __graft_entry__.build() /
+    tools/bake_selfcol.py); one host copy per process."""
+    if path not in _SELFCOL_CACHE:
+        if not os.path.exists(path):
+            raise _lib.BmiError("self-collision pair tables missing: %s (run `python tools/bake_selfcol.py` or "
+                                "__graft_entry__.build())" % path)
+        _SELFCOL_CACHE[path] = np.fromfile(path, dtype="<f4")
+    return _SELFCOL_CACHE[path]
 
 
 class BmiVecEnv:
@@ -20,7 +33,7 @@ class BmiVecEnv:
     distance_threshold = 0.05
     n_substeps = 20
 
-    def __init__(self, n_envs, task="push", seed=125, device=None, model_path=MODEL_PATH):
+    def __init__(self, n_envs, task="push", seed=125, device=None, model_path=MODEL_PATH, selfcol_path=SELFCOL_PATH):
         self.n_envs = int(n_envs)
         self.task = {"push": _lib.TASK_PUSH, "pick": _lib.TASK_PICK}[task]
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -30,6 +43,9 @@ class BmiVecEnv:
         _lib.call("bmi_env_create", ctypes.byref(h), self.n_envs, self.task, blob.ctypes.data_as(ctypes.c_void_p),
                   int(blob.nbytes))
         self._h = h
+        if blob[47] > 0.5:   # MP_SELF_COLLISION (bmirobot.py:58 flags=9)
+            t = _selfcol_table(selfcol_path)
+            _lib.call("bmi_env_set_selfcol", h, t.ctypes.data_as(ctypes.c_void_p), int(t.nbytes))
         f = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
         self.obs, self.ag, self.g = f(n_envs, 27), f(n_envs, 3), f(n_envs, 3)
         self.reward, self.success = f(n_envs), f(n_envs)
@@ -73,12 +89,10 @@ class BmiVecEnv:
         return self.obs, self.ag, self.reward, self.success
 
     def rollout(self, T, actor_t, o_norm, g_norm, clip_range, explore, noise_eps=0.0, random_eps=0.0, late_clip=0.0,
-                seed=0, counter=None, episodes=None, reset=True, queue=None):
+                seed=0, counter=None, episodes=None, reset=True):
         """Fused rollout: ONE kernel launch runs T policy + env steps for every env (bmi_env_rollout).
         actor_t: transposed flat actor parameters (bmi_actor_transpose); o_norm/g_norm: normalizer objects;
-        episodes: dict of float32 staging tensors obs/ag/g/actions or None.  Returns (obs, ag, g, success).
-        queue=(express_blocks, express_warps) runs the EXPERIMENTAL task-queue kernel (bmi_env_rollout_queue: same
-        episodes bit for bit, env-steps scheduled dynamically) instead."""
+        episodes: dict of float32 staging tensors obs/ag/g/actions or None.  Returns (obs, ag, g, success)."""
         if reset:
             _lib.call("bmi_env_sample_init", self._h, ctypes.c_uint64(self.seed_value), _lib.ptr(self.counter),
                       _lib.ptr(self.init), _lib.stream_ptr())
@@ -91,11 +105,14 @@ class BmiVecEnv:
                               float(noise_eps), float(random_eps), float(late_clip), int(seed), _lib.ptr(counter),
                               ctypes.pointer(eps) if eps is not None else None, _lib.ptr(self.init) if reset else None,
                               _lib.ptr(self.obs), _lib.ptr(self.ag), _lib.ptr(self.g), _lib.ptr(self.success))
-        if queue is not None:
-            _lib.call("bmi_env_rollout_queue", self._h, ctypes.byref(ra), int(queue[0]), int(queue[1]), _lib.stream_ptr())
-        else:
-            _lib.call("bmi_env_rollout", self._h, ctypes.byref(ra), _lib.stream_ptr())
+        _lib.call("bmi_env_rollout", self._h, ctypes.byref(ra), _lib.stream_ptr())
         return self.obs, self.ag, self.g, self.success
+
+    def contact_drops(self, reset=False):
+        """contacts dropped by the kernel's lane budget (9 contacts, 6 on arm links) since the counter was last reset"""
+        out = ctypes.c_uint64(0)
+        _lib.call("bmi_env_contact_drops", self._h, ctypes.byref(out), int(bool(reset)))
+        return int(out.value)
 
     def get_state(self):
         st = torch.empty((self.n_envs, _lib.ENV_STATE_DIM), dtype=torch.float32, device=self.device)

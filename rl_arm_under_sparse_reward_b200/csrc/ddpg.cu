@@ -332,8 +332,11 @@ __global__ void adam_kernel(float* __restrict__ pa, float* __restrict__ pc, cons
 // reads the gradient buffers of all ranks directly (peer loads), adds them in rank order (so every rank computes
 // the identical sum) and applies Adam to its own replica.  Cross-GPU ordering uses two flag barriers in peer
 // memory: "ready" (all backward passes have finished) before the reads, "done" (all ranks have finished reading)
-// before anyone may overwrite its gradients again.  Spins are bounded (about one second) and raise a timeout flag
-// instead of hanging the GPU.
+// before anyone may overwrite its gradients again.  Spins are bounded (about 30 s of SM clocks: host skew between ranks
+// -- first-call module loads, checkpoint I/O on rank 0 -- is seconds at most) so a dead peer cannot hang the GPU.  A
+// time-out is FATAL and sticky: the kernel returns WITHOUT touching the parameters (a partial gradient sum would make
+// the replicas diverge silently), every later launch returns immediately, and the host raises at the next check
+// (ddpg_agent.update_many / learn -> p2p_timed_out()).
 struct P2PArgs {
   const float* grads[8];
   int* sync[8];
@@ -352,7 +355,7 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
 __device__ __forceinline__ bool spin_until_ge(const int* p, int target, int* timeout_flag) {
   const long long t0 = clock64();
   while (ld_acquire_sys(p) < target) {
-    if (clock64() - t0 > 2000000000ll) {
+    if (clock64() - t0 > 60000000000ll || ld_acquire_sys(timeout_flag) != 0) {
       *timeout_flag = 1;
       return false;
     }
@@ -365,22 +368,25 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(P2PArgs pa, float* __rest
                                                        int64_t na_pad, int64_t n, const float* __restrict__ scal, float b1,
                                                        float b2, float eps) {
   int* mine = pa.sync[pa.rank];
+  if (ld_acquire_sys(mine + PS_TIMEOUT) != 0) return;   // sticky: a previous launch timed out, the replica is frozen
   const int epoch = mine[PS_EPOCH] + 1;   // written only by the last block of the previous launch (stream ordered)
-  __shared__ int ok;
+  __shared__ int ok_s;
+  if (threadIdx.x == 0) ok_s = 1;
+  __syncthreads();
   if (blockIdx.x == 0) {
     // "ready": tell every rank that this rank's gradients are complete, then wait for everybody
     if (threadIdx.x < pa.world) {
       __threadfence_system();
       st_release_sys(pa.sync[threadIdx.x] + PS_READY + pa.rank, epoch);
-      spin_until_ge(mine + PS_READY + threadIdx.x, epoch, mine + PS_TIMEOUT);
+      if (!spin_until_ge(mine + PS_READY + threadIdx.x, epoch, mine + PS_TIMEOUT)) ok_s = 0;
     }
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(mine + PS_GO, epoch);
+    if (threadIdx.x == 0) st_release_sys(mine + PS_GO, ok_s ? epoch : 0x7fffffff);   // 0x7fffffff releases the waiters into the abort path
   } else {
-    if (threadIdx.x == 0) spin_until_ge(mine + PS_GO, epoch, mine + PS_TIMEOUT);
+    if (threadIdx.x == 0 && !spin_until_ge(mine + PS_GO, epoch, mine + PS_TIMEOUT)) ok_s = 0;
     __syncthreads();
   }
-  (void)ok;
+  if (!ok_s || ld_acquire_sys(mine + PS_TIMEOUT) != 0) return;   // whole block: no Adam on a partial sum
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     if (i >= na && i < na_pad) continue;
     float gi = 0.f;

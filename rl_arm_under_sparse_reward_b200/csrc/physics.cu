@@ -93,7 +93,8 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
   float Rb[9], Ibinv[9];
   // contacts
   float cx[MAXC][3], cn[MAXC][3], cdist[MAXC], cmu[MAXC];
-  int clink[MAXC], chasb[MAXC], carm[MAXC];   // carm: arm slot of a contact or -1
+  int cinfo[MAXC];                // packed: link of body 2 (+1), block flag, arm-Jacobian slot (+1), link of body 1 of a self-contact (+2)
+  int pad_c[2];
   // Coupling table of the constraint solver.  Row x (one per contact row, x = 3 c + k) holds what a unit impulse on
   // that row does to every solver variable: [0, 9) the joint velocities (M^-1 Ja^T), [9, 15) the block velocity,
   // [15 + y] the constraint-space velocity of contact row y (the Delassus entry J_y M^-1 J_x^T).
@@ -127,13 +128,39 @@ struct __align__(16) Smem {      // per-env (per-warp) working set
   float obs[BMI_OBS_DIM + BMI_GOAL_DIM];   // last observation + achieved goal (fused rollout)
   float qik[NL];
   int prof_e;
-  int it_sum;                     // solver iterations since the env-step began (routing key of the task-queue rollout)
+  // warm start of the block-table island (substep_solve): impulses of the previous sub-step's block-table contacts and
+  // the block vertices they belong to (one byte each, 0xff = none); invalidated at the start of every env-step
+  float blk_lam[12];
+  unsigned blk_ids;
 };
 
+// one baked self-collision pair table (include/bmi_model.h SC_*), passed in kernel-parameter space
+struct SCPair {
+  int la, lb, ja, jb, na, nb;
+  unsigned off;
+  float a0, b0, inv_h, mu;
+};
 struct EnvParams {
   int task;
   float bh[3], bmass, binertia[3], bmu;
+  int sc_np;                       // self-collision pair tables in use (0: none loaded)
+  unsigned long long* drops;       // contacts dropped by the MAXC / MAXA lane budget (statistics)
 };
+// The pair-table descriptors live in constant memory (one table set per process: the robot model is a process-wide
+// asset); kernel-parameter space would be copied to the local stack as soon as EnvParams is passed by reference.
+__constant__ SCPair c_scp[BMI_SC_MAX_PAIRS];
+__constant__ const float* c_sc_data;
+
+// packed contact record: body 2 = arm link `link` or -1 (static world); hasb: body 1 is the block; arm: slot of the
+// contact's arm-Jacobian scratch rows or -1; linkA: body 1 of an arm self-contact (-1 = the base link), -2 otherwise
+__device__ __forceinline__ int c_pack(int link, int hasb, int arm, int linkA) {
+  return (link + 1) | (hasb << 4) | ((arm + 1) << 5) | ((linkA + 2) << 9);
+}
+__device__ __forceinline__ int c_link(int i) { return (i & 15) - 1; }
+__device__ __forceinline__ int c_hasb(int i) { return (i >> 4) & 1; }
+__device__ __forceinline__ int c_arm(int i) { return ((i >> 5) & 15) - 1; }
+__device__ __forceinline__ int c_linkA(int i) { return ((i >> 9) & 15) - 2; }
+__device__ __forceinline__ int c_vid(int i) { return (i >> 13) & 7; }   // block vertex of a block-table contact
 
 __device__ __forceinline__ float P(const Smem& s, int i) { return s.model[i]; }
 __device__ __forceinline__ const float* LK(const Smem& s, int i) { return s.model + BMI_MODEL_HDR + i * LINK_STRIDE_DEV; }
@@ -538,33 +565,99 @@ __device__ __noinline__ unsigned select_deepest(float d, bool valid, float margi
   return picked;
 }
 
-__device__ __noinline__ void push_contacts(Smem& s, unsigned mask, int lane, int link, int hasb, const float* x,
-                                              const float* n, float dist, float mu) {
+// linkA_of: per-lane body 1 of a self-contact (>= -1), or -2 for contacts against the table / the block
+__device__ __noinline__ void push_contacts(Smem& s, const EnvParams& ep, unsigned mask, int lane, int link, int hasb, const float* x,
+                                              const float* n, float dist, float mu, int linkA_of = -2) {
   if (mask == 0) return;
   const int base = s.nc, abase = s.na;
   // capacity: MAXC contacts in total, MAXA of them on arm links; later candidates (lane order) are dropped
   int allowed = MAXC - base;
-  if (link >= 0) allowed = min(allowed, MAXA - abase);
+  const bool arm = link >= 0 || linkA_of > -2;   // uniform per call (self-contacts come in their own call)
+  if (arm) allowed = min(allowed, MAXA - abase);
   const int rank = __popc(mask & ((1u << lane) - 1));
   const int n_add = min(__popc(mask), max(allowed, 0));
   if (((mask >> lane) & 1u) && rank < n_add) {
     const int slot = base + rank;
     s.cx[slot][0] = x[0]; s.cx[slot][1] = x[1]; s.cx[slot][2] = x[2];
     s.cn[slot][0] = n[0]; s.cn[slot][1] = n[1]; s.cn[slot][2] = n[2];
-    s.cdist[slot] = dist; s.cmu[slot] = mu; s.clink[slot] = link; s.chasb[slot] = hasb;
-    s.carm[slot] = link >= 0 ? abase + rank : -1;
+    s.cdist[slot] = dist; s.cmu[slot] = mu;
+    s.cinfo[slot] = c_pack(link, hasb, arm ? abase + rank : -1, linkA_of) | ((hasb && link < 0) ? (lane << 13) : 0);   // block vertex id
   }
+  if (lane == 0 && n_add < __popc(mask) && ep.drops) atomicAdd(ep.drops, (unsigned long long)(__popc(mask) - n_add));
   __syncwarp();
   if (lane == 0) {
     s.nc = base + n_add;
-    if (link >= 0) s.na = abase + n_add;
+    if (arm) s.na = abase + n_add;
   }
   __syncwarp();
 }
 
+// ---- self-collision of the arm: baked pair tables (tools/bake_selfcol.py; oracle: find_self_contacts / sc_lookup) ------
+// Every link pair that can touch is two joints apart, so the whole narrow phase (signed distance of the two hulls,
+// normal, witness point) is a function of two joint angles, sampled off line with the oracle's GJK + EPA on a 5 mrad
+// grid.  Here: lane = (pair p = lane / 8, node c = (lane / 2) % 4 of the surrounding cell, half = lane % 2 of the
+// node's 32-byte record), so ONE coalesced 16-byte load per lane fetches all four cells of all four pairs; bilinear when
+// the four nodes describe the same hull features (normals within 1.8 degrees, witness points within 2 mm), else the
+// nearest node (feature switches are kinks of the distance function; the wrist rests on one).
+__device__ __noinline__ void self_contacts(Smem& s, const EnvParams& ep, int lane) {
+  const int p = lane >> 3, c = (lane >> 1) & 3, half = lane & 1;
+  const bool live = p < ep.sc_np;
+  const SCPair& d = c_scp[live ? p : 0];
+  float fa = (s.q[d.ja] - d.a0) * d.inv_h, fb = (s.q[d.jb] - d.b0) * d.inv_h;
+  fa = fminf(fmaxf(fa, 0.f), (float)(d.na - 1));
+  fb = fminf(fmaxf(fb, 0.f), (float)(d.nb - 1));
+  const int i = min((int)fa, d.na - 2), j = min((int)fb, d.nb - 2);
+  const float wa = fa - (float)i, wb = fb - (float)j;
+  const int near = (wa >= 0.5f ? 2 : 0) + (wb >= 0.5f ? 1 : 0);
+  float4 v = make_float4(1e3f, 0.f, 0.f, 0.f);
+  if (live) v = __ldg(reinterpret_cast<const float4*>(c_sc_data + d.off) + 2 * ((size_t)(i + (c >> 1)) * d.nb + (j + (c & 1))) + half);
+  const int src = (lane & ~7) | (near << 1) | half;
+  const float4 vn = make_float4(__shfl_sync(FULL, v.x, src), __shfl_sync(FULL, v.y, src), __shfl_sync(FULL, v.z, src), __shfl_sync(FULL, v.w, src));
+  bool ok;
+  if (half == 0) ok = v.x < 100.f && v.y * vn.y + v.z * vn.z + v.w * vn.w >= 0.9995f;
+  else { const float dx = v.x - vn.x, dy = v.y - vn.y, dz = v.z - vn.z; ok = dx * dx + dy * dy + dz * dz <= 4e-6f; }
+  const bool same = ((__ballot_sync(FULL, ok) >> (lane & ~7)) & 0xffu) == 0xffu;
+  const float w = ((c & 2) ? wa : 1.f - wa) * ((c & 1) ? wb : 1.f - wb);
+  float4 a = make_float4(w * v.x, w * v.y, w * v.z, w * v.w);
+#pragma unroll
+  for (int o = 2; o <= 4; o <<= 1) {
+    a.x += __shfl_xor_sync(FULL, a.x, o); a.y += __shfl_xor_sync(FULL, a.y, o);
+    a.z += __shfl_xor_sync(FULL, a.z, o); a.w += __shfl_xor_sync(FULL, a.w, o);
+  }
+  if (!same) a = vn;
+  // the leader lane of each pair (lane % 8 == 0: half 0) collects the witness point from its neighbour (half 1)
+  const float xl0 = __shfl_down_sync(FULL, a.x, 1), xl1 = __shfl_down_sync(FULL, a.y, 1), xl2 = __shfl_down_sync(FULL, a.z, 1);
+  const float far = __shfl_sync(FULL, vn.x, (lane & ~7) | (near << 1));   // nearest node's distance (sentinel test)
+  float dist = 0.f, nw[3] = {0.f, 0.f, 0.f}, xw[3] = {0.f, 0.f, 0.f};
+  bool valid = false;
+  if (live && (lane & 7) == 0 && far < 100.f) {
+    float nl[3] = {a.y, a.z, a.w};
+    if (same) { const float r = rsqrtf(dot3(nl, nl)); nl[0] *= r; nl[1] *= r; nl[2] *= r; }
+    const float xl[3] = {xl0, xl1, xl2};
+    dist = a.x - 2.f * P(s, MP_HULL_MARGIN);
+    if (!(dist > P(s, MP_SELF_NEAR))) {
+      valid = true;
+      if (d.la >= 0) {
+        mat_vec(nw, s.R[d.la], nl);
+        mat_vec(xw, s.R[d.la], xl);
+        xw[0] += s.p[d.la][0]; xw[1] += s.p[d.la][1]; xw[2] += s.p[d.la][2];
+      } else {  // right_link1 is rigid with the base: identity rotation at the base position
+        nw[0] = nl[0]; nw[1] = nl[1]; nw[2] = nl[2];
+        xw[0] = xl[0] + P(s, MP_BASE_PX); xw[1] = xl[1] + P(s, MP_BASE_PY); xw[2] = xl[2] + P(s, MP_BASE_PZ);
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(FULL, valid);
+  push_contacts(s, ep, m, lane, d.lb, 0, xw, nw, dist, d.mu, live ? d.la : -2);
+}
+
 __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const float* __restrict__ model_g,
-                                           float block_margin, int lane) {
+                                           float block_margin, bool with_self, int lane) {
   if (lane == 0) { s.nc = 0; s.na = 0; }
+  __syncwarp();
+  // the arm's self-contacts come first (Bullet keeps its manifolds in creation order: the robot is loaded before the
+  // table and the block), which also keeps them inside the lane budget
+  if (with_self && ep.sc_np > 0 && P(s, MP_SELF_COLLISION) > 0.5f) self_contacts(s, ep, lane);
   // block frame
   if (lane == 0) {
     const float x = s.bq[0], y = s.bq[1], z = s.bq[2], w = s.bq[3];
@@ -585,7 +678,7 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
   {  // block vertices vs table plane, up to 4 deepest
     const float d = bvx[2] - tz;
     unsigned m = select_deepest(d, lane < 8, P(s, MP_TABLE_MARGIN), 4, lane);
-    push_contacts(s, m, lane, -1, 1, bvx, up, d, ep.bmu * P(s, MP_MU_TABLE));
+    push_contacts(s, ep, m, lane, -1, 1, bvx, up, d, ep.bmu * P(s, MP_MU_TABLE));
   }
   const int ns = (int)P(s, MP_N_SHAPES);
   const float* shapes = s.model + (int)P(s, MP_SHAPES_OFF);   // staged in shared memory with the joint tree
@@ -616,7 +709,7 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
     if (near_table) {  // hull vertices vs table plane, up to 2 deepest
       const float d = wv[2] - tz;
       unsigned m = select_deepest(d, lane < nv, P(s, MP_CONTACT_MARGIN), 2, lane);
-      push_contacts(s, m, lane, l, 0, wv, up, d, smu * P(s, MP_MU_TABLE));
+      push_contacts(s, ep, m, lane, l, 0, wv, up, d, smu * P(s, MP_MU_TABLE));
     }
     if (!near_block) continue;
     // candidates: lanes 0..7 = block vertex vs hull planes, lanes 8..8+nv-1 = hull vertex vs block box
@@ -660,7 +753,7 @@ __device__ __noinline__ void find_contacts(Smem& s, const EnvParams& ep, const f
     }
     // (hull polytopes are baked with <= 24 vertices, so 8 + nv <= 32 candidates fit one warp)
     unsigned m = select_deepest(d, valid, block_margin, 3, lane);
-    push_contacts(s, m, lane, l, 1, x, nrm, d, ep.bmu * smu);
+    push_contacts(s, ep, m, lane, l, 1, x, nrm, d, ep.bmu * smu);
   }
   __syncwarp();
 }
@@ -714,7 +807,7 @@ __device__ __noinline__ void substep_dynamics(Smem& s, const EnvParams& ep, cons
     s.u[lane] = s.bw[a] + dt * (-(ka + ka * wn) * s.bw[a]);
   } else if (lane == 15) s.u[15] = 0.f;
   PROF_ADD(s.prof_e, 3);
-  find_contacts(s, ep, model_g, P(s, MP_BLOCK_MARGIN), lane);
+  find_contacts(s, ep, model_g, P(s, MP_BLOCK_MARGIN), true, lane);
   PROF_ADD(s.prof_e, 4);
   if (lane < 9) {  // world-frame inverse inertia of the block: R diag(1/I) R^T
     const int r = lane / 3, cc = lane % 3;
@@ -757,8 +850,8 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lane) {
   PROF_T0();
   const float dt = P(s, MP_DT);
-  const int nc = s.nc, nrows = 3 * nc;
-  const bool has_arm = s.na > 0;        // uniform
+  const int nc = (int)__reduce_max_sync(FULL, (unsigned)s.nc), nrows = 3 * nc;   // REDUX: provably warp-uniform
+  const bool has_arm = __ballot_sync(FULL, s.na > 0) != 0u;   // warp-uniform by construction (ballot)
   float v0 = 0.f, v1 = 0.f, v2 = 0.f;   // solver variables of this lane
   float lam0 = 0.f, lam1 = 0.f, lam2 = 0.f, dl0 = 0.f, dl1 = 0.f, dl2 = 0.f;
   float rhs0 = 0.f, rhs1 = 0.f, rhs2 = 0.f, inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, dg0 = 0.f, dg1 = 0.f, dg2 = 0.f;
@@ -793,28 +886,53 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
 #pragma unroll
     for (int a = 0; a < 3; ++a) dir[a] = kind == 0 ? n[a] : (kind == 1 ? t1[a] : t2[a]);
     const float x[3] = {s.cx[ci][0], s.cx[ci][1], s.cx[ci][2]};
-    const int link = s.clink[ci], hasb = s.chasb[ci];
+    const int info = s.cinfo[ci];
+    const int link = c_link(info), hasb = c_hasb(info), linkA = c_linkA(info);
     float* Srow = s.S + lane * SS;
     float diag = 0.f, rel = 0.f;
     if (link >= 0) {  // arm part, compact runtime loops through this row's scratch slot
       const float sgn = hasb ? -1.f : 1.f;
-      my_as = s.carm[ci] * 3 + kind;
+      my_as = c_arm(info) * 3 + kind;
       float* Jr = s.rows.Ja[my_as];
-      for (int j = 0; j < NL; ++j) Jr[j] = 0.f;
+      float diag_sum = 0.f;
+      // Self-contact (linkA > -2): body 1 = linkA at the witness x, body 2 = link at x2 = x - n * (core distance).
+      // Two passes over the same scratch row: first J_A + J_B (only its quadratic form is needed), then the row's real
+      // Jacobian J_A - J_B.  Bullet's diagonal for two links of ONE multibody is J_A M^-1 J_A^T + J_B M^-1 J_B^T (no
+      // cross term, btMultiBodyConstraintSolver::setupMultiBodyContactConstraint) = the mean of the two quadratic forms.
+      const bool self = linkA > -2;
+      const float dcore = s.cdist[ci] + 2.f * P(s, MP_HULL_MARGIN);
+      const float x2[3] = {x[0] - n[0] * dcore, x[1] - n[1] * dcore, x[2] - n[2] * dcore};
 #pragma unroll 1
-      for (int j = link; j >= 0; j = parent_of(j)) {  // joints on the path base -> link
-        float r[3] = {x[0] - s.p[j][0], x[1] - s.p[j][1], x[2] - s.p[j][2]}, cr[3];
-        cross3(cr, s.z[j], r);
-        Jr[j] = sgn * dot3(dir, cr);
-      }
+      for (int pass = self ? 0 : 1; pass < 2; ++pass) {
+        for (int j = 0; j < NL; ++j) Jr[j] = 0.f;
+        const float sb = self ? (pass == 0 ? 1.f : -1.f) : sgn;   // sign of body 2's part
 #pragma unroll 1
-      for (int i = 0; i < NL; ++i) {
-        float acc = 0.f;
-        for (int j = 0; j < NL; ++j) acc += MINV(s, i, j) * Jr[j];
-        Srow[i] = acc;
-        diag += Jr[i] * acc;
-        rel += Jr[i] * s.u[i];
+        for (int j = link; j >= 0; j = parent_of(j)) {  // joints on the path base -> link
+          const float* xx = self ? x2 : x;
+          float r[3] = {xx[0] - s.p[j][0], xx[1] - s.p[j][1], xx[2] - s.p[j][2]}, cr[3];
+          cross3(cr, s.z[j], r);
+          Jr[j] = sb * dot3(dir, cr);
+        }
+        if (self) {
+#pragma unroll 1
+          for (int j = linkA; j >= 0; j = parent_of(j)) {
+            float r[3] = {x[0] - s.p[j][0], x[1] - s.p[j][1], x[2] - s.p[j][2]}, cr[3];
+            cross3(cr, s.z[j], r);
+            Jr[j] += dot3(dir, cr);
+          }
+        }
+        diag = 0.f; rel = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < NL; ++i) {
+          float acc = 0.f;
+          for (int j = 0; j < NL; ++j) acc += MINV(s, i, j) * Jr[j];
+          Srow[i] = acc;
+          diag += Jr[i] * acc;
+          rel += Jr[i] * s.u[i];
+        }
+        if (pass == 0) diag_sum = diag;
       }
+      if (self && P(s, MP_SELF_SPLIT_DIAG) > 0.5f) diag = 0.5f * (diag + diag_sum);
     } else {
 #pragma unroll
       for (int i = 0; i < NL; ++i) Srow[i] = 0.f;
@@ -888,8 +1006,60 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
     ja = s_base + (unsigned)(3 * myc) * (SS * 4u);
     ca = s_base + (unsigned)(SCOL_CT + 3 * myc) * 4u;
   }
-  const int max_it = (int)P(s, MP_SOLVER_ITERS);
+  int max_it = (int)P(s, MP_SOLVER_ITERS);
   const float thresh = P(s, MP_RESIDUAL_THRESH);
+  const bool alternate = __reduce_max_sync(FULL, P(s, MP_SWEEP_ALTERNATE) > 0.5f ? 1u : 0u) != 0u;
+  // ---- iteration schedule ------------------------------------------------------------------------------------------
+  // (a) Compression (oracle: substep(), MP_PGS_COMPRESS).  The arm's self-contact rows carry Bullet's same-multibody
+  //     diagonal, 1e3 .. 3e3 times the true one: over the 150 iterations their impulses grow as an almost linear ramp
+  //     (the loop never converges: that softness IS the reference's wrist) and every other row tracks the ramp with one
+  //     iteration of lag.  n_c iterations with K-fold steps on those rows followed by `tail` plain ones land on the same
+  //     point: K n_c + tail = MP_SOLVER_ITERS equivalent iterations.
+  // (b) Block island: while no arm link touches the block, the block-table rows form a separate island that converges
+  //     in 20-30 iterations; once its residual is below the threshold its rows are skipped (Bullet keeps sweeping them
+  //     with impulse changes below 3e-4 x the row diagonal).
+  unsigned self_mask = 0u, blk_mask = 0u, armblk_mask = 0u;   // per contact slot
+  {
+    const int info = lane < nc ? s.cinfo[lane] : 0;
+    self_mask = __ballot_sync(FULL, lane < nc && c_linkA(info) > -2);
+    blk_mask = __ballot_sync(FULL, lane < nc && c_hasb(info) && c_link(info) < 0);
+    armblk_mask = __ballot_sync(FULL, lane < nc && c_hasb(info) && c_link(info) >= 0);
+  }
+  const float Kc = P(s, MP_PGS_COMPRESS);
+  int n_c = 0;
+  if (Kc > 1.f && self_mask) {
+    n_c = (int)((float)(max_it - (int)P(s, MP_PGS_TAIL)) / Kc);
+    max_it = n_c + (max_it - (int)((float)n_c * Kc));
+  }
+  max_it = (int)__reduce_max_sync(FULL, (unsigned)max_it);   // provably warp-uniform loop bounds
+  n_c = (int)__reduce_max_sync(FULL, (unsigned)n_c);
+  const bool own_ct = myc >= 0 && myc < nc;
+  const float kself = (own_ct && ((self_mask >> myc) & 1u)) ? Kc : 1.f;
+  const bool blk_lane = own_ct && ((blk_mask >> myc) & 1u);
+  const bool blk_island = armblk_mask == 0u && blk_mask != 0u;
+  unsigned skip_mask = 0u;      // contact slots whose rows are no longer swept
+  // (c) Warm start of the block island: its converged solution does not depend on the starting point, so the rows start
+  //     from the previous sub-step's impulses (same block vertex on the table) and are done after 1-3 sweeps instead of
+  //     ~45 from zero.  Only while the island is decoupled from the arm; Bullet's cold start otherwise.
+  if (blk_island) {
+    const unsigned ids = s.blk_ids;
+    if (blk_lane) {
+      const int vid = c_vid(s.cinfo[myc]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((int)((ids >> (8 * k)) & 0xffu) == vid) { lam0 = s.blk_lam[3 * k]; lam1 = s.blk_lam[3 * k + 1]; lam2 = s.blk_lam[3 * k + 2]; }
+    }
+    if (__ballot_sync(FULL, blk_lane && lam0 != 0.f)) {
+      for (unsigned m = blk_mask; m; m &= m - 1u) {
+        const int c = __ffs(m) - 1;
+        const float l0 = __shfl_sync(FULL, lam0, LANE_CT + c), l1 = __shfl_sync(FULL, lam1, LANE_CT + c), l2 = __shfl_sync(FULL, lam2, LANE_CT + c);
+        const unsigned a = ca + (unsigned)c * (3u * SS * 4u);
+        v0 = fmaf(lds_f(a), l0, v0); v1 = fmaf(lds_f(a + 4u), l0, v1); v2 = fmaf(lds_f(a + 8u), l0, v2);
+        v0 = fmaf(lds_f(a + SS * 4u), l1, v0); v1 = fmaf(lds_f(a + SS * 4u + 4u), l1, v1); v2 = fmaf(lds_f(a + SS * 4u + 8u), l1, v2);
+        v0 = fmaf(lds_f(a + 2u * SS * 4u), l2, v0); v1 = fmaf(lds_f(a + 2u * SS * 4u + 4u), l2, v1); v2 = fmaf(lds_f(a + 2u * SS * 4u + 8u), l2, v2);
+      }
+    }
+  }
   int it = 0;
   PROF_ADD(s.prof_e, 5);
   // one joint-source update: every lane adds its coefficient x d (contact lanes: all three rows, only when some
@@ -903,19 +1073,14 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
     }                                                                                     \
     v0 = fmaf(c0_, (dj), v0);                                                             \
   } while (0)
-  // motors (J = e_j, bounds +-max_imp), then violated joint limits (J = +-e_j, bounds [0, hi])
-#define BMI_JOINT_ROWS(ARM)                                                               \
+  // motors (J = e_j, bounds +-max_imp), then violated joint limits (J = +-e_j, bounds [0, hi]).  Bullet sweeps these
+  // non-contact rows BACKWARDS on even iterations (btMultiBodyConstraintSolver::solveSingleIteration: index =
+  // iteration & 1 ? j : size - 1 - j): limits from the highest joint down, then motors 8 .. 0.
+#define BMI_LIMIT_ROWS(ARM, FWD)                                                          \
   do {                                                                                    \
-    _Pragma("unroll (kMotorUnroll)")                                                      \
-    for (int j = 0; j < NL; ++j) {                                                        \
-      const float cand = fminf(fmaxf(lam0 + fmaf(-v0, inv0, rhs0), -max_imp), max_imp);   \
-      const float d = cand - lam0;                                                        \
-      const float dj = __shfl_sync(FULL, d, j);                                           \
-      if (lane == j) { lam0 = cand; dl0 = d; }                                            \
-      BMI_JOINT_EVENT(ARM, 4u * j, dj);                                                   \
-    }                                                                                     \
-    for (unsigned m = limit_mask; m; m &= m - 1u) {                                       \
-      const int j = __ffs(m) - 1;                                                         \
+    for (unsigned m = limit_mask; m;) {                                                   \
+      const int j = (FWD) ? __ffs(m) - 1 : 31 - __clz(m);                                 \
+      m &= ~(1u << j);                                                                    \
       const float cand = fminf(fmaxf(lam1 + fmaf(-v0, inv1, rhs1), 0.f), lim_hi);         \
       const float d = cand - lam1;                                                        \
       const float dj = __shfl_sync(FULL, d * lsgn, j);                                    \
@@ -923,34 +1088,52 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
       BMI_JOINT_EVENT(ARM, 4u * (unsigned)j, dj);                                         \
     }                                                                                     \
   } while (0)
+#define BMI_JOINT_ROWS(ARM)                                                               \
+  do {                                                                                    \
+    const bool fwd_ = !alternate || (it & 1);                                             \
+    if (!fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, false);                                  \
+    _Pragma("unroll (kMotorUnroll)")                                                      \
+    for (int jj = 0; jj < NL; ++jj) {                                                     \
+      const int j = fwd_ ? jj : NL - 1 - jj;                                              \
+      const float cand = fminf(fmaxf(lam0 + fmaf(-v0, inv0, rhs0), -max_imp), max_imp);   \
+      const float d = cand - lam0;                                                        \
+      const float dj = __shfl_sync(FULL, d, j);                                           \
+      if (lane == j) { lam0 = cand; dl0 = d; }                                            \
+      BMI_JOINT_EVENT(ARM, 4u * (unsigned)j, dj);                                         \
+    }                                                                                     \
+    if (fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, true);                                    \
+  } while (0)
+  unsigned active = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);   // contact slots still swept (bit c)
+  float kf = n_c > 0 ? kself : 1.f;
 #pragma unroll 1
   while (true) {
+    if (it == n_c) kf = 1.f;   // uniform: end of the compressed phase
 #if BMI_SOLVE_SINGLE_VARIANT
     BMI_JOINT_ROWS(true);
 #else
     if (has_arm) BMI_JOINT_ROWS(true); else BMI_JOINT_ROWS(false);
 #endif
-    // ---- contact normals (unrolled over the contact slot: static shuffle lane, owner test and table offset) -------
-#pragma unroll (kContactUnroll)
-    for (int c = 0; c < MAXC; ++c) {
-      if (c >= nc) break;   // uniform
+    // ---- contact normals: only the slots still swept (rolled: the body must stay inside the L0 instruction cache) ----
+#pragma unroll 1
+    for (unsigned m = active; m; m &= m - 1u) {
+      const int c = __ffs(m) - 1;
       const unsigned a = ca + (unsigned)c * (3u * SS * 4u);
       const float c0 = lds_f(a), c1 = lds_f(a + 4u), c2 = lds_f(a + 8u);
-      const float cand = fmaxf(lam0 + fmaf(-v0, inv0, rhs0), 0.f);
+      const float cand = fmaxf(fmaf(kf, fmaf(-v0, inv0, rhs0), lam0), 0.f);
       const float d = cand - lam0;
       const float dc = __shfl_sync(FULL, d, LANE_CT + c);
       if (myc == c) { lam0 = cand; dl0 = d; }
       v0 = fmaf(c0, dc, v0); v1 = fmaf(c1, dc, v1); v2 = fmaf(c2, dc, v2);
     }
     // ---- friction cones -------------------------------------------------------------------------------------------
-#pragma unroll (kContactUnroll)
-    for (int c = 0; c < MAXC; ++c) {
-      if (c >= nc) break;   // uniform
+#pragma unroll 1
+    for (unsigned m = active; m; m &= m - 1u) {
+      const int c = __ffs(m) - 1;
       const unsigned a = ca + (unsigned)c * (3u * SS * 4u) + SS * 4u;
       const float p0 = lds_f(a), p1 = lds_f(a + 4u), p2 = lds_f(a + 8u);
       const float q0 = lds_f(a + SS * 4u), q1 = lds_f(a + SS * 4u + 4u), q2 = lds_f(a + SS * 4u + 8u);
       const float lim = mu * lam0;
-      float sa = lam1 + fmaf(-v1, inv1, rhs1), sb = lam2 + fmaf(-v2, inv2, rhs2);
+      float sa = fmaf(kf, fmaf(-v1, inv1, rhs1), lam1), sb = fmaf(kf, fmaf(-v2, inv2, rhs2), lam2);
       const float n2 = sa * sa + sb * sb;
       const float sc = n2 > lim * lim ? lim * rsqrt_fast(n2) : 1.f;  // branch-free cone projection (x * 1 is exact)
       sa *= sc; sb *= sc;
@@ -961,16 +1144,36 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
       v0 = fmaf(q0, dbc, v0); v1 = fmaf(q1, dbc, v1); v2 = fmaf(q2, dbc, v2);
     }
     // ---- residual: max over all rows of (impulse change x row diagonal)^2 ------------------------------------------
-    const float r0 = dl0 * dg0, r1 = dl1 * dg1, r2 = dl2 * dg2;
-    const float rl = fmaxf(r0 * r0, fmaxf(r1 * r1, r2 * r2));
-    const float resid = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rl)));   // rl >= 0: uint order = float order
+    // With under-relaxed rows in the system the loop never meets Bullet's threshold (the oracle runs all iterations
+    // too): the global residual is only evaluated for models without them.
     ++it;
-    if (resid <= thresh || it >= max_it) break;
+    if (it >= max_it) break;
+    const bool want_blk = blk_island && skip_mask == 0u;
+    if (self_mask == 0u || want_blk) {
+      const float r0 = dl0 * dg0, r1 = dl1 * dg1, r2 = dl2 * dg2;
+      const float rl = fmaxf(r0 * r0, fmaxf(r1 * r1, r2 * r2));
+      if (self_mask == 0u) {
+        const float resid = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rl)));   // rl >= 0: uint order = float order
+        if (resid <= thresh) break;
+      }
+      if (want_blk) {   // the island is frozen 100x below Bullet's threshold (3e-5 m/s of row velocity change)
+        const float rb = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(blk_lane ? rl : 0.f)));
+        if (rb <= 1e-2f * thresh) { skip_mask = blk_mask; active &= ~blk_mask; }
+      }
+    }
   }
 #undef BMI_JOINT_ROWS
+#undef BMI_LIMIT_ROWS
 #undef BMI_JOINT_EVENT
   PROF_CNT(s.prof_e, 7, it);
-  if (lane == 0) s.it_sum += it;
+  {  // impulses of the block island for the next sub-step's warm start
+    const int slot = __popc(blk_mask & ((1u << (myc & 31)) - 1u));   // rank of this lane's contact among the block-table contacts
+    if (blk_island && blk_lane && slot < 4) { s.blk_lam[3 * slot] = lam0; s.blk_lam[3 * slot + 1] = lam1; s.blk_lam[3 * slot + 2] = lam2; }
+    unsigned idb = blk_island && blk_lane && slot < 4 ? ((unsigned)c_vid(s.cinfo[myc]) << (8 * slot)) | ~(0xffu << (8 * slot)) : 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) idb &= __shfl_xor_sync(FULL, idb, o);
+    if (lane == 0) s.blk_ids = idb;
+  }
   // ---- integrate --------------------------------------------------------------------------------------------------
   const float unew = lane < NU ? s.u[lane] + v0 : 0.f;
   if (lane < NL) {
@@ -1110,11 +1313,12 @@ __device__ __noinline__ void env_step_begin(Smem& s, const EnvParams& ep, const 
 #pragma unroll
   for (int i = 0; i < 4; ++i) a[i] = fminf(fmaxf(a_in[i], -0.5f), 0.5f);
   if (ep.task == BMI_TASK_PUSH) a[3] = 0.f;  // bmirobot_env_push_F.py:94
+  if (lane == 0) s.blk_ids = 0xffffffffu;    // every env-step starts the block island cold (step-wise == fused rollout)
   fk(s, s.q, lane);
   if (ep.task == BMI_TASK_PICK) {  // auto-grip (bmirobot_env_pickandplace_v2.py:94-95)
-    find_contacts(s, ep, model_g, 1e-4f, lane);
+    find_contacts(s, ep, model_g, 1e-4f, false, lane);
     bool touch = false;
-    for (int c = 0; c < s.nc; ++c) touch |= (s.chasb[c] && s.clink[c] >= 0 && s.cdist[c] < 1e-4f);
+    for (int c = 0; c < s.nc; ++c) touch |= (c_hasb(s.cinfo[c]) && c_link(s.cinfo[c]) >= 0 && s.cdist[c] < 1e-4f);
     if (touch) a[3] = -1.f;
   }
   // applyAction (bmirobot.py:129-162)
@@ -1345,128 +1549,6 @@ rollout_kernel(const float* __restrict__ model_g, unsigned model_bytes, EnvParam
   store_state(s, st, lane);
 }
 
-// ---- task-queue rollout (EXPERIMENTAL, Args.queue_rollout) ---------------------------------------------------------
-// Same episodes as rollout_kernel, bit for bit (every env-step is computed by rollout_step from the env's own state),
-// but a warp is not bound to an env: a task is ONE env-step (env, t).  q.word[env] packs
-//   bit 31: claimed   bits 30..16: solver iterations of the env's last step (routing key)   bits 15..0: steps done.
-// A free warp scans the words, claims an unclaimed env with steps left (atomicCAS), loads its 48-float state and last
-// observation from global memory, runs the step, stores, and releases the word with the new key.  The blocks
-// [0, express_blocks) are "express": only express_warps of their warps run, and they pick the env with the LARGEST key;
-// all other warps pick the smallest key (ties: fewest steps done).  An env whose hand rests on the table (2-3x the
-// solver iterations, for the whole episode) therefore migrates to an express SM where it shares a sub-partition with at
-// most one other warp, instead of setting the launch time from a fully loaded SM.
-// No warp ever waits for another one: a warp exits when no unclaimed env has steps left.
-struct QueueArgs {
-  unsigned* word;        // [n_envs]
-  float* obs_cache;      // [n_envs][BMI_OBS_DIM + BMI_GOAL_DIM]: observation + achieved goal after the env's last step
-  int express_blocks, express_warps;
-};
-
-__global__ void __launch_bounds__(32 * WARPS, BLOCKS_PER_SM)
-rollout_queue_kernel(const float* __restrict__ model_g, unsigned model_bytes, EnvParams ep, int n_envs,
-                     float* __restrict__ state, RolloutArgs ra, QueueArgs q) {
-  BlockSmem& bs = *reinterpret_cast<BlockSmem*>(bmi_dyn_smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  block_begin(bs, model_g, model_bytes);
-  const bool express = (int)blockIdx.x < q.express_blocks;
-  if (express && warp >= q.express_warps) return;
-  Smem& s = bs.sw[warp];
-  constexpr int Do = BMI_OBS_DIM, Dg = BMI_GOAL_DIM;
-  const PolicyW pw = policy_weights(ra);
-  const unsigned long long ctr0 = ra.explore ? *ra.counter : 0ull;
-  const unsigned T = (unsigned)ra.T;
-  // start the scan at a warp-specific offset so that simultaneous pickers do not all fight for the same entry
-  const int scan0 = (int)(((blockIdx.x * WARPS + warp) * 97u) % (unsigned)n_envs);
-  while (true) {
-    // ---- pick: best unclaimed env with steps left ------------------------------------------------------------------
-    unsigned best_key = 0u;   // larger = better; 0 = nothing found
-    int best_env = -1;
-    for (int i = lane; i < n_envs; i += 32) {
-      int e = scan0 + i;
-      if (e >= n_envs) e -= n_envs;
-      const unsigned w = __ldcg(q.word + e);
-      const unsigned done = w & 0xffffu, cost = (w >> 16) & 0x7fffu;
-      if ((w >> 31) == 0u && done < T) {
-        // express: most expensive first; bulk: cheapest first, then the env that is furthest behind
-        const unsigned key = express ? (1u + (cost << 16) + (0xffffu - done)) : (1u + ((0x7fffu - cost) << 16) + (0xffffu - done));
-        if (key > best_key) { best_key = key; best_env = e; }
-      }
-    }
-    const unsigned top = __reduce_max_sync(FULL, best_key);
-    if (top == 0u) break;   // nothing left to start (envs in flight are continued by the warps that hold them)
-    const int src = __ffs(__ballot_sync(FULL, best_key == top)) - 1;
-    const int e = __shfl_sync(FULL, best_env, src);
-    unsigned mine = 0u;
-    int ok = 0;
-    if (lane == 0) {
-      mine = __ldcg(q.word + e);
-      ok = (mine >> 31) == 0u && (mine & 0xffffu) < T && atomicCAS(q.word + e, mine, mine | 0x80000000u) == mine;
-    }
-    ok = __shfl_sync(FULL, ok, 0);
-    if (!ok) continue;      // somebody else was faster: rescan
-    const int t = (int)(__shfl_sync(FULL, mine, 0) & 0xffffu);
-    __threadfence();        // acquire: the previous holder's state / observation stores
-    // ---- load the env ------------------------------------------------------------------------------------------------
-    float* st = state + (size_t)e * BMI_ENV_STATE_DIM;
-    if (t == 0 && ra.init != nullptr) {  // reset (bmirobot_env_push_F.py:110-165)
-      const float* in = ra.init + (size_t)e * 8;
-      for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {
-        float v = 0.f;
-        if (i >= ST_BPOS && i < ST_BPOS + 3) v = in[i - ST_BPOS];
-        else if (i == ST_BQUAT + 2 || i == ST_BQUAT + 3) {
-          float sy, cy;
-          sincos_compact(0.5f * in[3], &sy, &cy);
-          v = i == ST_BQUAT + 2 ? sy : cy;
-        }
-        else if (i >= ST_GOAL && i < ST_GOAL + 3) v = in[4 + i - ST_GOAL];
-        st[i] = v;
-      }
-      __syncwarp();
-    }
-    for (int i = lane; i < BMI_ENV_STATE_DIM; i += 32) {   // load_state through L2 (the previous holder may sit on another SM)
-      const float v = __ldcg(st + i);
-      if (i < ST_QD) s.q[i - ST_Q] = v;
-      else if (i < ST_QT) s.qd[i - ST_QD] = v;
-      else if (i < ST_BPOS) s.qt[i - ST_QT] = v;
-      else if (i < ST_BQUAT) s.bp[i - ST_BPOS] = v;
-      else if (i < ST_BVEL) s.bq[i - ST_BQUAT] = v;
-      else if (i < ST_BANG) s.bv[i - ST_BVEL] = v;
-      else if (i < ST_GOAL) s.bw[i - ST_BANG] = v;
-      else if (i < ST_PAD) s.goal[i - ST_GOAL] = v;
-    }
-    __syncwarp();
-    if (t == 0) observe(s, lane, s.obs, s.obs + Do);
-    else {
-      if (lane < Do + Dg) s.obs[lane] = __ldcg(q.obs_cache + (size_t)e * (Do + Dg) + lane);
-      __syncwarp();
-    }
-    if (lane == 0) s.it_sum = 0;
-    __syncwarp();
-    // ---- the step -----------------------------------------------------------------------------------------------------
-    rollout_step(s, ep, model_g, ra, pw, ctr0, n_envs, e, t, lane);
-    // ---- store, release ------------------------------------------------------------------------------------------------
-    store_state(s, st, lane);
-    if (lane < Do + Dg) q.obs_cache[(size_t)e * (Do + Dg) + lane] = s.obs[lane];
-    if (t + 1 == ra.T) {
-      if (ra.ep_obs) {
-        if (lane < Do) ra.ep_obs[((size_t)e * (ra.T + 1) + ra.T) * Do + lane] = s.obs[lane];
-        if (lane < Dg) ra.ep_ag[((size_t)e * (ra.T + 1) + ra.T) * Dg + lane] = s.obs[Do + lane];
-      }
-      if (ra.obs && lane < Do) ra.obs[(size_t)e * Do + lane] = s.obs[lane];
-      if (ra.ag && lane < Dg) ra.ag[(size_t)e * Dg + lane] = s.obs[Do + lane];
-      if (ra.g && lane < Dg) ra.g[(size_t)e * Dg + lane] = s.goal[lane];
-      if (ra.success && lane == 0) ra.success[e] = goal_dist(s) < P(s, MP_DIST_THRESHOLD) ? 1.f : 0.f;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const unsigned cost = (unsigned)min(s.it_sum, 0x7fff);
-      __threadfence();      // release: state / observation before the word
-      atomicExch(q.word + e, (cost << 16) | (unsigned)(t + 1));
-    }
-    __syncwarp();
-  }
-}
-
 // W[out][in] (torch layout) -> Wt[in][out]
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int n_out, int n_in) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1552,8 +1634,9 @@ struct bmi_env {
   float* state_dev = nullptr;
   int64_t model_floats = 0;
   unsigned model_bytes = 0;     // staged size: the blob rounded up to 16 bytes
-  unsigned* queue_word = nullptr;   // task-queue rollout: one word per env (lazily allocated)
-  float* queue_obs = nullptr;       // ... and the observation cache
+  bool self_collision = false;  // MP_SELF_COLLISION of the blob
+  float* sc_dev = nullptr;          // self-collision pair tables (bmi_env_set_selfcol)
+  unsigned long long* drops_dev = nullptr;
 };
 
 extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const void* blob, int64_t bytes) {
@@ -1584,7 +1667,6 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   {  // the env kernels keep ENVW env working sets per block in dynamic shared memory (> 48 KB: opt-in)
     BMI_CUDA_CHECK(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem)));
     BMI_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem)));
-    BMI_CUDA_CHECK(cudaFuncSetAttribute(rollout_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmem)));
   }
   bmi_env* h = new bmi_env();
   h->n_envs = n_envs;
@@ -1594,6 +1676,7 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   for (int a = 0; a < 3; ++a) h->ep.bh[a] = b[o + a];
   h->ep.bmass = b[o + 3];
   h->ep.bmu = b[o + 4];
+  h->ep.sc_np = 0; h->ep.drops = nullptr;
   const float lx = 2 * h->ep.bh[0], ly = 2 * h->ep.bh[1], lz = 2 * h->ep.bh[2], mm = h->ep.bmass / 12.f;
   h->ep.binertia[0] = mm * (ly * ly + lz * lz);
   h->ep.binertia[1] = mm * (lx * lx + lz * lz);
@@ -1619,7 +1702,54 @@ extern "C" int bmi_env_create(bmi_env** out, int32_t n_envs, int32_t task, const
   }
   BMI_CUDA_CHECK(cudaMemcpy(h->model_dev, dev.data(), h->model_bytes, cudaMemcpyHostToDevice));
   BMI_CUDA_CHECK(cudaMemset(h->state_dev, 0, (size_t)n_envs * BMI_ENV_STATE_DIM * sizeof(float)));
+  if (cudaMalloc(&h->drops_dev, sizeof(unsigned long long)) == cudaSuccess) {
+    BMI_CUDA_CHECK(cudaMemset(h->drops_dev, 0, sizeof(unsigned long long)));
+    h->ep.drops = h->drops_dev;
+  }
+  h->self_collision = b[MP_SELF_COLLISION] > 0.5f;
   *out = h;
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_set_selfcol(bmi_env* h, const void* table, int64_t bytes) {
+  BMI_REQUIRE(h && table, "bmi_env_set_selfcol: null pointer");
+  BMI_REQUIRE(bytes >= (int64_t)((SC_HDR + SC_DESC) * sizeof(float)) && bytes % 16 == 0, "bmi_env_set_selfcol: bad table size");
+  const float* t = (const float*)table;
+  const int np = (int)t[SC_NPAIRS];
+  BMI_REQUIRE(t[SC_MAGIC] == BMI_SC_MAGIC && (int64_t)t[SC_TOTAL] * 4 == bytes && np >= 1 && np <= BMI_SC_MAX_PAIRS,
+              "bmi_env_set_selfcol: table magic / size / pair count mismatch");
+  SCPair scp[BMI_SC_MAX_PAIRS] = {};
+  for (int p = 0; p < np; ++p) {
+    const float* d = t + SC_HDR + SC_DESC * p;
+    SCPair& o = scp[p];
+    o.la = (int)d[SC_LA]; o.lb = (int)d[SC_LB]; o.ja = (int)d[SC_JA]; o.jb = (int)d[SC_JB];
+    o.na = (int)d[SC_NA]; o.nb = (int)d[SC_NB]; o.off = (unsigned)d[SC_OFF];
+    o.a0 = d[SC_A0]; o.b0 = d[SC_B0]; o.inv_h = 1.f / d[SC_H]; o.mu = d[SC_MU];
+    BMI_REQUIRE(o.la >= -1 && o.la < NL && o.lb >= 0 && o.lb < NL && o.ja >= 0 && o.ja < NL && o.jb >= 0 && o.jb < NL &&
+                    o.na >= 2 && o.nb >= 2 && o.off % 4 == 0 && (int64_t)o.off + 8ll * o.na * o.nb <= bytes / 4,
+                "bmi_env_set_selfcol: bad descriptor of pair %d", p);
+  }
+  if (h->sc_dev) cudaFree(h->sc_dev);
+  h->sc_dev = nullptr;
+  BMI_CUDA_CHECK(cudaMalloc(&h->sc_dev, (size_t)bytes));
+  BMI_CUDA_CHECK(cudaMemcpy(h->sc_dev, table, (size_t)bytes, cudaMemcpyHostToDevice));
+  const float* data = h->sc_dev;
+  BMI_CUDA_CHECK(cudaMemcpyToSymbol(c_scp, scp, sizeof(scp)));
+  BMI_CUDA_CHECK(cudaMemcpyToSymbol(c_sc_data, &data, sizeof(data)));
+  h->ep.sc_np = np;
+  return BMI_OK;
+}
+
+extern "C" int bmi_env_contact_drops(bmi_env* h, uint64_t* host_out, int32_t reset) {
+  BMI_REQUIRE(h && h->drops_dev, "bmi_env_contact_drops: no counter");
+  if (host_out) BMI_CUDA_CHECK(cudaMemcpy(host_out, h->drops_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) BMI_CUDA_CHECK(cudaMemset(h->drops_dev, 0, sizeof(uint64_t)));
+  return BMI_OK;
+}
+
+// a model with self-collision switched on must not be stepped without its pair tables (no silent degradation)
+static int require_tables(const bmi_env* h, const char* who) {
+  BMI_REQUIRE(!h->self_collision || h->ep.sc_np > 0, "%s: the model enables self-collision but no pair tables are loaded (bmi_env_set_selfcol)", who);
   return BMI_OK;
 }
 
@@ -1627,8 +1757,8 @@ extern "C" int bmi_env_destroy(bmi_env* h) {
   if (!h) return BMI_OK;
   if (h->model_dev) cudaFree(h->model_dev);
   if (h->state_dev) cudaFree(h->state_dev);
-  if (h->queue_word) cudaFree(h->queue_word);
-  if (h->queue_obs) cudaFree(h->queue_obs);
+  if (h->sc_dev) cudaFree(h->sc_dev);
+  if (h->drops_dev) cudaFree(h->drops_dev);
   delete h;
   return BMI_OK;
 }
@@ -1656,6 +1786,7 @@ extern "C" int bmi_env_sample_init(bmi_env* h, uint64_t seed, uint64_t* counter,
 extern "C" int bmi_env_step(bmi_env* h, const float* actions, float* obs, float* ag, float* reward, float* success,
                             bmi_stream_t stream) {
   BMI_REQUIRE(h && actions && obs && ag, "bmi_env_step: null pointer");
+  if (int rc = require_tables(h, "bmi_env_step")) return rc;
   env_step_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), as_stream(stream)>>>(h->model_dev, h->model_bytes, h->ep, h->n_envs, h->state_dev,
                                                                                           actions, obs, ag, reward, success);
   BMI_LAUNCHED();
@@ -1721,35 +1852,9 @@ extern "C" int bmi_env_rollout(bmi_env* h, const bmi_rollout_args* a, bmi_stream
   RolloutArgs ra;
   const int rc = fill_rollout_args(h, a, ra, "bmi_env_rollout");
   if (rc != BMI_OK) return rc;
+  if (int rc2 = require_tables(h, "bmi_env_rollout")) return rc2;
   cudaStream_t st = as_stream(stream);
   rollout_kernel<<<(h->n_envs + ENVW - 1) / ENVW, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->model_bytes, h->ep, h->n_envs, h->state_dev, ra);
-  BMI_LAUNCHED();
-  if (a->explore) {
-    advance_counter_kernel3<<<1, 1, 0, st>>>(a->counter, (uint64_t)a->T * (uint64_t)h->n_envs);
-    BMI_LAUNCHED();
-  }
-  return BMI_OK;
-}
-
-extern "C" int bmi_env_rollout_queue(bmi_env* h, const bmi_rollout_args* a, int32_t express_blocks, int32_t express_warps,
-                                     bmi_stream_t stream) {
-  RolloutArgs ra;
-  const int rc = fill_rollout_args(h, a, ra, "bmi_env_rollout_queue");
-  if (rc != BMI_OK) return rc;
-  const int blocks = (h->n_envs + ENVW - 1) / ENVW;
-  BMI_REQUIRE(a->T < 65536, "bmi_env_rollout_queue: T must be below 65536");
-  BMI_REQUIRE(express_blocks >= 0 && express_blocks < blocks + (blocks == 1) && express_warps >= 1 && express_warps <= ENVW,
-              "bmi_env_rollout_queue: express_blocks must be in [0, %d) and express_warps in [1, %d]", blocks, ENVW);
-  if (blocks == 1) express_blocks = 0;   // a single block must keep all its warps
-  if (!h->queue_word) {
-    BMI_CUDA_CHECK(cudaMalloc(&h->queue_word, (size_t)h->n_envs * sizeof(unsigned)));
-    BMI_CUDA_CHECK(cudaMalloc(&h->queue_obs, (size_t)h->n_envs * (BMI_OBS_DIM + BMI_GOAL_DIM) * sizeof(float)));
-  }
-  cudaStream_t st = as_stream(stream);
-  BMI_CUDA_CHECK(cudaMemsetAsync(h->queue_word, 0, (size_t)h->n_envs * sizeof(unsigned), st));
-  QueueArgs q;
-  q.word = h->queue_word; q.obs_cache = h->queue_obs; q.express_blocks = express_blocks; q.express_warps = express_warps;
-  rollout_queue_kernel<<<blocks, 32 * WARPS, sizeof(BlockSmem), st>>>(h->model_dev, h->model_bytes, h->ep, h->n_envs, h->state_dev, ra, q);
   BMI_LAUNCHED();
   if (a->explore) {
     advance_counter_kernel3<<<1, 1, 0, st>>>(a->counter, (uint64_t)a->T * (uint64_t)h->n_envs);

@@ -147,9 +147,21 @@ class ddpg_agent:
         except ImportError:
             pass
 
+    def _resolve_demo(self):
+        """args.demo_name as given (cwd, like the reference), else next to the package / the repo root"""
+        name = self.args.demo_name
+        here = os.path.dirname(os.path.abspath(__file__))
+        for cand in (name, os.path.join(here, name), os.path.join(os.path.dirname(here), name)):
+            if os.path.exists(cand):
+                return cand
+        raise FileNotFoundError(
+            "add_demo=True but the demo file %r was not found (cwd, %s, %s).  Copy the reference's .npz there or "
+            "generate one with `python -m rl_arm_under_sparse_reward_b200.get_demo_data --task push --n 1000`; "
+            "Args.add_demo=False trains without demonstrations." % (name, here, os.path.dirname(here)))
+
     def _init_demo_buffer(self):
         """ddpg_agent.py:82-90: preload the expert episodes (normalisers are NOT updated from them)."""
-        demo = np.load(self.args.demo_name, allow_pickle=True)
+        demo = np.load(self._resolve_demo(), allow_pickle=True)
         self.buffer.store_episode([np.array(demo['obs']), np.array(demo['ag']), np.array(demo['g']), np.array(demo['acs'])])
 
     # ---- rollout -------------------------------------------------------------------------------------
@@ -208,9 +220,7 @@ class ddpg_agent:
                   _lib.ptr(self._actor_t), _lib.stream_ptr())
         self.vec.rollout(self.T, self._actor_t, self.o_norm, self.g_norm, self.args.clip_range, explore,
                          noise_eps=self.args.noise_eps, random_eps=self.args.random_eps, late_clip=late_clip,
-                         seed=self._seed, counter=self._ctr_explore, episodes=self.ep if explore else None,
-                         queue=((int(getattr(self.args, 'queue_express_blocks', 0)), int(getattr(self.args, 'queue_express_warps', 8)))
-                                if getattr(self.args, 'queue_rollout', False) else None))
+                         seed=self._seed, counter=self._ctr_explore, episodes=self.ep if explore else None)
 
     def rollout(self, epoch=0):
         """One batch of R simultaneous episodes (ddpg_agent.py:103-141); fills self.ep.  Default: the fused
@@ -261,9 +271,16 @@ class ddpg_agent:
 
     # ---- updates ---------------------------------------------------------------------------------------
     def _soft_update_target_network(self, target=None, source=None):
-        """ddpg_agent.py:220-222; one call updates both target nets (arguments kept for API parity)."""
-        if target is None or target is self.actor_target_network:
+        """ddpg_agent.py:220-222.  Without arguments: both target nets in one fused launch (what learn() uses).  With the
+        reference's (target, source) arguments: that one net, target <- (1 - polyak) source + polyak target with the
+        reference's rounding (two products, one sum)."""
+        if target is None and source is None:
             _lib.call("bmi_ddpg_soft_update", self._h, _lib.stream_ptr())
+            return
+        if target is None or source is None or target.flat.shape != source.flat.shape:
+            raise ValueError("_soft_update_target_network(target, source): both networks of the same architecture, or neither")
+        p = float(self.args.polyak)
+        target.flat.copy_((1 - p) * source.flat + p * target.flat)
 
     def _update_body(self, draws=None):
         a, st, b = self.args, _lib.stream_ptr(), self.buffer
@@ -321,6 +338,13 @@ class ddpg_agent:
         self._run_graphed(("update", n), body)
         self.updates += n
 
+    def check_p2p(self):
+        """utils.py:43-48 semantics must hold on every update: a timed-out peer-memory gradient sum is fatal (the kernel
+        froze this replica's parameters instead of applying a partial sum)."""
+        if self._p2p and self.p2p_timed_out():
+            raise RuntimeError("fused peer-memory gradient sum timed out: a peer rank stopped responding; the "
+                               "replicas are no longer synchronised (restart, or set Args.p2p_adam=False for NCCL)")
+
     def release_graphs(self):
         """Drop the captured CUDA graphs (they hold references to the NCCL communicator)."""
         torch.cuda.synchronize()
@@ -342,6 +366,7 @@ class ddpg_agent:
                 self._update_normalizer()
                 self.update_many(a.n_batches)
                 self._soft_update_target_network()
+                self.check_p2p()
             torch.cuda.synchronize()
             if getattr(a, "verbose", True):
                 print(str(time.time() - start_time))
@@ -369,14 +394,20 @@ class ddpg_agent:
     def _eval_agent(self):
         """ddpg_agent.py:280-304: noise-free episodes, success = is_success at the LAST step, averaged over
         ranks.  ceil(n_test_rollouts / R) batches of R simultaneous episodes."""
-        n_batches = max(1, -(-int(self.args.n_test_rollouts) // self.R))
+        n_test = int(self.args.n_test_rollouts)
+        if getattr(self.args, "eval_all_envs", False):     # vectorised runs: every env of the batch is an eval episode
+            n_test = max(n_test, self.R)
+        n_batches = max(1, -(-n_test // self.R))
         total = torch.zeros((), dtype=torch.float32, device=self.device)
+        left = n_test
         for _ in range(n_batches):
             if getattr(self.args, "fused_rollout", True):
                 self._fused_rollout_body(False, 0.0)
             else:
                 self._run_graphed(("eval",), self._eval_body)
-            total += self.vec.success.mean()
-        local = torch.stack([total / n_batches]).contiguous()
+            k = min(left, self.R)              # exactly n_test_rollouts episodes count (the reference runs 25, not 26)
+            total += self.vec.success[:k].sum()
+            left -= k
+        local = torch.stack([total / n_test]).contiguous()
         utils.allreduce_sum_(local)
         return float(local.item()) / utils.world_size()

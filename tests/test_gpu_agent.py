@@ -154,18 +154,49 @@ def test_pick_task_cycle_with_demo_preload(tmp_path, golden_dir):
     assert (z > 0.19).all() and (z < 0.30).all()
 
 
-@pytest.mark.parametrize("express", [(0, 8), (1, 4)])
-def test_task_queue_rollout_reproduces_the_fused_rollout_bit_for_bit(tmp_path, express):
-    """EXPERIMENTAL bmi_env_rollout_queue: env-steps are scheduled dynamically (any warp, any SM, express blocks for
-    the expensive envs) but every step is computed from the env's own state, so the episodes must be identical."""
-    ag1, _ = _agent(tmp_path, n_envs=96)
-    ag2, _ = _agent(tmp_path, n_envs=96, queue_rollout=True, queue_express_blocks=express[0], queue_express_warps=express[1])
-    ag2.actor_network.flat.copy_(ag1.actor_network.flat)
-    for ag in (ag1, ag2):
-        ag.rollout(0)
-        ag.rollout(0)          # second batch: fresh placements, Philox counters advanced
-    torch.cuda.synchronize()
-    for k in ("obs", "ag", "g", "actions"):
-        assert torch.equal(ag1.ep[k], ag2.ep[k]), k
-    assert torch.equal(ag1.vec.success, ag2.vec.success) and torch.equal(ag1.vec.obs, ag2.vec.obs)
-    assert torch.equal(ag1.vec.get_state(), ag2.vec.get_state())
+def test_launch_learn_one_epoch_with_reference_demo_and_checkpoint(tmp_path, golden_dir, monkeypatch):
+    """train.launch() -> ddpg_agent.learn() end to end (train.py:26-45, ddpg_agent.py:92-161): add_demo with a slice of the
+    reference's own demo file, 1 epoch x 2 cycles at 64 envs, per-epoch eval, checkpoint in the reference's tuple layout
+    that the reference's demo_push.py loader accepts (models.py state_dict keys), success_rates saved by
+    plot_success_rate()."""
+    from rl_arm_under_sparse_reward_b200 import train
+    from rl_arm_under_sparse_reward_b200.arguments import Args
+    monkeypatch.chdir(tmp_path)
+    a = Args()
+    a.n_envs, a.n_epochs, a.n_cycles, a.n_batches, a.verbose = 64, 1, 2, 3, False
+    a.buffer_size, a.save_dir = 256 * 100, str(tmp_path) + "/saved_models/"
+    a.add_demo, a.demo_name = True, os.path.join(golden_dir, "demo_small.npz")
+    tr = train.launch(a)
+    assert tr.buffer.current_size == 16 + 2 * 64 and tr.env_steps == 2 * 64 * 100 and tr.updates == 6
+    assert len(tr.success_rates) == 1 and 0.0 <= tr.success_rates[0] <= 1.0
+    assert os.path.exists(tmp_path / "test_rates" / ("%d_True_success_rates.npy" % a.seed))
+    ckpt = [f for f in os.listdir(tr.model_path) if f.endswith("_model.pt")]
+    assert len(ckpt) == 1
+    o_mean, o_std, g_mean, g_std, sd = torch.load(os.path.join(tr.model_path, ckpt[0]), weights_only=False)
+    assert np.asarray(o_mean).shape == (27,) and np.asarray(g_std).shape == (3,)
+    ref = torch.nn.ModuleDict({"fc1": torch.nn.Linear(30, 256), "fc2": torch.nn.Linear(256, 256), "fc3": torch.nn.Linear(256, 256),
+                               "action_out": torch.nn.Linear(256, 4)})   # the reference actor's layers (models.py:15-18)
+    ref.load_state_dict(sd)
+    # a missing demo file fails with a message that says what to do (Args() default: add_demo=True, cwd-relative name)
+    b = Args()
+    b.n_envs, b.verbose, b.save_dir, b.demo_name = 8, False, str(tmp_path) + "/m2/", "does_not_exist.npz"
+    from rl_arm_under_sparse_reward_b200.bmirobot_env.vec_env import BmiVecEnv
+    from rl_arm_under_sparse_reward_b200.ddpg_agent import ddpg_agent
+    with pytest.raises(FileNotFoundError, match="get_demo_data"):
+        ddpg_agent(b, BmiVecEnv(8), train.get_env_params(None) if False else {'obs': 27, 'goal': 3, 'action': 4, 'action_max': 0.5, 'max_timesteps': 100})
+
+
+def test_soft_update_honours_target_and_source(tmp_path):
+    """ddpg_agent.py:220-222 with the reference's (target, source) arguments updates exactly that net"""
+    ag, a = _agent(tmp_path, n_envs=8)
+    ag.actor_network.flat.add_(0.25)
+    ag.critic_network.flat.add_(0.5)
+    at, ct = ag.actor_target_network.flat.clone(), ag.critic_target_network.flat.clone()
+    ag._soft_update_target_network(ag.critic_target_network, ag.critic_network)
+    assert torch.equal(ag.actor_target_network.flat, at)
+    want = (1 - a.polyak) * ag.critic_network.flat + a.polyak * ct
+    assert torch.equal(ag.critic_target_network.flat, want)
+    ag._soft_update_target_network(ag.actor_target_network, ag.actor_network)
+    assert torch.equal(ag.actor_target_network.flat, (1 - a.polyak) * ag.actor_network.flat + a.polyak * at)
+    with pytest.raises(ValueError):
+        ag._soft_update_target_network(ag.actor_target_network, None)

@@ -10,9 +10,6 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 a = Args()
-if os.environ.get("BMI_QUEUE"):   # "express_blocks,express_warps": the experimental task-queue rollout
-    a.queue_rollout = True
-    a.queue_express_blocks, a.queue_express_warps = [int(x) for x in os.environ["BMI_QUEUE"].split(",")]
 a.add_demo, a.verbose, a.n_envs, a.buffer_size, a.save_dir = False, False, n, 8192 * 100, "/tmp/bmi_prof/"
 torch.manual_seed(125)
 env = BmiVecEnv(n, seed=125)
