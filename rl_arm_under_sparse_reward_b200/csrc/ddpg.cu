@@ -96,7 +96,7 @@ struct bmi_ddpg {
   float *ah1 = nullptr, *ah2 = nullptr, *ah3 = nullptr, *az = nullptr, *aa = nullptr;  // actor(x)
   float *qh1 = nullptr, *qh2 = nullptr, *qh3 = nullptr, *qa = nullptr, *xca = nullptr; // critic(x, pi(x))
   float *a_next = nullptr, *q_next = nullptr, *y = nullptr;
-  float *d1 = nullptr, *d2 = nullptr, *dq = nullptr, *dxc = nullptr, *dz = nullptr;    // backward scratch
+  float *d1 = nullptr, *d2 = nullptr, *dq = nullptr, *dq_const = nullptr, *dxc = nullptr, *dz = nullptr;    // backward scratch
   // policy (act) activations (max_act_rows)
   float *ph1 = nullptr, *ph2 = nullptr, *pz = nullptr;
   std::vector<void*> owned;
@@ -194,6 +194,19 @@ __global__ void concat_scale_kernel(const float* __restrict__ x, const float* __
   xc[i] = j < Dx ? x[r * Dx + j] : __fdiv_rn(a[r * Da + (j - Dx)], amax);
 }
 
+// a = amax tanh(z) and xc[r] = [x[r], a[r] / amax] in one pass (the actor head feeding a critic input)
+__global__ void tanh_concat_kernel(const float* __restrict__ x, const float* __restrict__ z, int n, int Dx, int Da,
+                                   float amax, float* __restrict__ a_out, float* __restrict__ xc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int D = Dx + Da;
+  if (i >= n * D) return;
+  int r = i / D, j = i % D;
+  if (j < Dx) { xc[i] = x[r * Dx + j]; return; }
+  const float a = amax * tanhf(z[r * Da + (j - Dx)]);
+  a_out[r * Da + (j - Dx)] = a;
+  xc[i] = __fdiv_rn(a, amax);
+}
+
 __global__ void tanh_scale_kernel(const float* __restrict__ z, int n, float amax,
                                   float* __restrict__ a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,13 +234,17 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
   return t;  // valid in warp 0
 }
 
+// target y = clamp(r + gamma q', -1/(1-gamma), 0) (ddpg_agent.py:255-260) fused with
 // critic loss = mean((y - q)^2); dq = 2 (q - y) / B          single block
-__global__ void critic_loss_kernel(const float* __restrict__ y, const float* __restrict__ q, int B,
+__global__ void critic_loss_kernel(const float* __restrict__ r, const float* __restrict__ qn, float gamma, float clip_ret,
+                                   const float* __restrict__ q, int B, float* __restrict__ y_out,
                                    float* __restrict__ dq, float* __restrict__ loss) {
   __shared__ float sm[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    float d = y[i] - q[i];
+    const float yi = fminf(fmaxf(__fadd_rn(r[i], __fmul_rn(gamma, qn[i])), -clip_ret), 0.0f);
+    y_out[i] = yi;
+    float d = yi - q[i];
     acc += d * d;
     dq[i] = -2.0f * d / (float)B;
   }
@@ -552,10 +569,14 @@ extern "C" int bmi_ddpg_create(bmi_ddpg** out, const bmi_ddpg_config* cfg, float
   A_(ah1, B * H); A_(ah2, B * H); A_(ah3, B * H); A_(az, B * Da); A_(aa, B * Da);
   A_(qh1, B * H); A_(qh2, B * H); A_(qh3, B * H); A_(qa, B); A_(xca, B * (Dx + Da));
   A_(a_next, B * Da); A_(q_next, B); A_(y, B);
-  A_(d1, B * H); A_(d2, B * H); A_(dq, B > H ? B : H); A_(dxc, B * (Dx + Da)); A_(dz, B * Da > H ? B * Da : H);
+  A_(d1, B * H); A_(d2, B * H); A_(dq, B > H ? B : H); A_(dq_const, B); A_(dxc, B * (Dx + Da)); A_(dz, B * Da > H ? B * Da : H);
   A_(ph1, (size_t)cfg->max_act_rows * H); A_(ph2, (size_t)cfg->max_act_rows * H);
   A_(pz, (size_t)cfg->max_act_rows * Da);
 #undef A_
+  if (!rc) {   // d(-mean Q)/dQ of the actor loss: constant, written once
+    fill_kernel<<<(B + 255) / 256, 256>>>(h->dq_const, B, -1.0f / (float)B);
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("bmi_ddpg_create: fill failed"); rc = BMI_ERR_CUDA; }
+  }
   if (!rc) {
     void* p = nullptr;
     if (cudaMalloc(&p, sizeof(int)) != cudaSuccess || cudaMemset(p, 0, sizeof(int)) != cudaSuccess) {
@@ -631,34 +652,27 @@ extern "C" int bmi_ddpg_backward(bmi_ddpg* h, const float* x, const float* xn, c
   // ---- target: y = clamp(r + gamma * Q'(x', pi'(x')), -1/(1-gamma), 0) -------------------
   if ((rc = mlp_hidden(h, st, h->la, h->actor_t, xn, B, h->h1, h->h2, h->h3))) return rc;
   if ((rc = mlp_out(h, st, h->la, h->actor_t, h->h3, B, h->az))) return rc;
-  tanh_scale_kernel<<<(B * Da + 255) / 256, 256, 0, st>>>(h->az, B * Da, amax, h->a_next);
-  BMI_LAUNCHED();
-  concat_scale_kernel<<<(B * Dc + 255) / 256, 256, 0, st>>>(xn, h->a_next, B, Dx, Da, amax, h->xc);
+  tanh_concat_kernel<<<(B * Dc + 255) / 256, 256, 0, st>>>(xn, h->az, B, Dx, Da, amax, h->a_next, h->xc);
   BMI_LAUNCHED();
   if ((rc = mlp_hidden(h, st, h->lc, h->critic_t, h->xc, B, h->h1, h->h2, h->h3))) return rc;
   if ((rc = mlp_out(h, st, h->lc, h->critic_t, h->h3, B, h->q_next))) return rc;
-  target_kernel<<<(B + 255) / 256, 256, 0, st>>>(r, h->q_next, B, c.gamma, c.clip_return, h->y);
-  BMI_LAUNCHED();
   // ---- critic loss + backward -----------------------------------------------------------
   concat_scale_kernel<<<(B * Dc + 255) / 256, 256, 0, st>>>(x, actions, B, Dx, Da, amax, h->xc);
   BMI_LAUNCHED();
   if ((rc = mlp_hidden(h, st, h->lc, h->critic, h->xc, B, h->ch1, h->ch2, h->ch3))) return rc;
   if ((rc = mlp_out(h, st, h->lc, h->critic, h->ch3, B, h->q))) return rc;
-  critic_loss_kernel<<<1, 256, 0, st>>>(h->y, h->q, B, h->dq, losses + 1);
+  critic_loss_kernel<<<1, 256, 0, st>>>(r, h->q_next, c.gamma, c.clip_return, h->q, B, h->y, h->dq, losses + 1);
   BMI_LAUNCHED();
   if ((rc = mlp_backward(h, st, h->lc, h->critic, Gc, h->xc, h->ch1, h->ch2, h->ch3, h->dq, B, nullptr))) return rc;
   // ---- actor loss + backward ------------------------------------------------------------
   if ((rc = mlp_hidden(h, st, h->la, h->actor, x, B, h->ah1, h->ah2, h->ah3))) return rc;
   if ((rc = mlp_out(h, st, h->la, h->actor, h->ah3, B, h->az))) return rc;
-  tanh_scale_kernel<<<(B * Da + 255) / 256, 256, 0, st>>>(h->az, B * Da, amax, h->aa);
-  BMI_LAUNCHED();
-  concat_scale_kernel<<<(B * Dc + 255) / 256, 256, 0, st>>>(x, h->aa, B, Dx, Da, amax, h->xca);
+  tanh_concat_kernel<<<(B * Dc + 255) / 256, 256, 0, st>>>(x, h->az, B, Dx, Da, amax, h->aa, h->xca);
   BMI_LAUNCHED();
   if ((rc = mlp_hidden(h, st, h->lc, h->critic, h->xca, B, h->qh1, h->qh2, h->qh3))) return rc;
   if ((rc = mlp_out(h, st, h->lc, h->critic, h->qh3, B, h->qa))) return rc;
-  fill_kernel<<<(B + 255) / 256, 256, 0, st>>>(h->dq, B, -1.0f / (float)B);
-  BMI_LAUNCHED();
-  if ((rc = mlp_backward(h, st, h->lc, h->critic, nullptr, h->xca, h->qh1, h->qh2, h->qh3, h->dq, B, h->dxc))) return rc;
+  // d(-mean Q)/dQ = -1/B: a constant vector, filled once at creation (dq_const)
+  if ((rc = mlp_backward(h, st, h->lc, h->critic, nullptr, h->xca, h->qh1, h->qh2, h->qh3, h->dq_const, B, h->dxc))) return rc;
   actor_loss_kernel<<<1, 256, 0, st>>>(h->qa, h->aa, h->dxc, B, Dx, Da, amax, c.action_l2, h->dz, losses);
   BMI_LAUNCHED();
   // dz now holds the gradient wrt the actor's output pre-activation; mlp_backward with G

@@ -1076,7 +1076,7 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   // motors (J = e_j, bounds +-max_imp), then violated joint limits (J = +-e_j, bounds [0, hi]).  Bullet sweeps these
   // non-contact rows BACKWARDS on even iterations (btMultiBodyConstraintSolver::solveSingleIteration: index =
   // iteration & 1 ? j : size - 1 - j): limits from the highest joint down, then motors 8 .. 0.
-#define BMI_LIMIT_ROWS(ARM, FWD)                                                          \
+#define BMI_LIMIT_ROWS(ARM, FWD, TRACK)                                                        \
   do {                                                                                    \
     for (unsigned m = limit_mask; m;) {                                                   \
       const int j = (FWD) ? __ffs(m) - 1 : 31 - __clz(m);                                 \
@@ -1084,84 +1084,85 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
       const float cand = fminf(fmaxf(lam1 + fmaf(-v0, inv1, rhs1), 0.f), lim_hi);         \
       const float d = cand - lam1;                                                        \
       const float dj = __shfl_sync(FULL, d * lsgn, j);                                    \
-      if (lane == j) { lam1 = cand; dl1 = d; }                                            \
+      if (lane == j) { lam1 = cand; if (TRACK) dl1 = d; }                                 \
       BMI_JOINT_EVENT(ARM, 4u * (unsigned)j, dj);                                         \
     }                                                                                     \
   } while (0)
-#define BMI_JOINT_ROWS(ARM)                                                               \
+#define BMI_JOINT_ROWS(ARM, TRACK)                                                             \
   do {                                                                                    \
     const bool fwd_ = !alternate || (it & 1);                                             \
-    if (!fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, false);                                  \
+    if (!fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, false, TRACK);                               \
     _Pragma("unroll (kMotorUnroll)")                                                      \
     for (int jj = 0; jj < NL; ++jj) {                                                     \
       const int j = fwd_ ? jj : NL - 1 - jj;                                              \
       const float cand = fminf(fmaxf(lam0 + fmaf(-v0, inv0, rhs0), -max_imp), max_imp);   \
       const float d = cand - lam0;                                                        \
       const float dj = __shfl_sync(FULL, d, j);                                           \
-      if (lane == j) { lam0 = cand; dl0 = d; }                                            \
+      if (lane == j) { lam0 = cand; if (TRACK) dl0 = d; }                                 \
       BMI_JOINT_EVENT(ARM, 4u * (unsigned)j, dj);                                         \
     }                                                                                     \
-    if (fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, true);                                    \
+    if (fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, true, TRACK);                                 \
   } while (0)
   unsigned active = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);   // contact slots still swept (bit c)
   float kf = n_c > 0 ? kself : 1.f;
-#pragma unroll 1
-  while (true) {
-    if (it == n_c) kf = 1.f;   // uniform: end of the compressed phase
-#if BMI_SOLVE_SINGLE_VARIANT
-    BMI_JOINT_ROWS(true);
-#else
-    if (has_arm) BMI_JOINT_ROWS(true); else BMI_JOINT_ROWS(false);
-#endif
-    // ---- contact normals: only the slots still swept (rolled: the body must stay inside the L0 instruction cache) ----
-#pragma unroll 1
-    for (unsigned m = active; m; m &= m - 1u) {
-      const int c = __ffs(m) - 1;
-      const unsigned a = ca + (unsigned)c * (3u * SS * 4u);
-      const float c0 = lds_f(a), c1 = lds_f(a + 4u), c2 = lds_f(a + 8u);
-      const float cand = fmaxf(fmaf(kf, fmaf(-v0, inv0, rhs0), lam0), 0.f);
-      const float d = cand - lam0;
-      const float dc = __shfl_sync(FULL, d, LANE_CT + c);
-      if (myc == c) { lam0 = cand; dl0 = d; }
-      v0 = fmaf(c0, dc, v0); v1 = fmaf(c1, dc, v1); v2 = fmaf(c2, dc, v2);
-    }
-    // ---- friction cones -------------------------------------------------------------------------------------------
-#pragma unroll 1
-    for (unsigned m = active; m; m &= m - 1u) {
-      const int c = __ffs(m) - 1;
-      const unsigned a = ca + (unsigned)c * (3u * SS * 4u) + SS * 4u;
-      const float p0 = lds_f(a), p1 = lds_f(a + 4u), p2 = lds_f(a + 8u);
-      const float q0 = lds_f(a + SS * 4u), q1 = lds_f(a + SS * 4u + 4u), q2 = lds_f(a + SS * 4u + 8u);
-      const float lim = mu * lam0;
-      float sa = fmaf(kf, fmaf(-v1, inv1, rhs1), lam1), sb = fmaf(kf, fmaf(-v2, inv2, rhs2), lam2);
-      const float n2 = sa * sa + sb * sb;
-      const float sc = n2 > lim * lim ? lim * rsqrt_fast(n2) : 1.f;  // branch-free cone projection (x * 1 is exact)
-      sa *= sc; sb *= sc;
-      const float da = sa - lam1, db = sb - lam2;
-      const float dac = __shfl_sync(FULL, da, LANE_CT + c), dbc = __shfl_sync(FULL, db, LANE_CT + c);
-      if (myc == c) { lam1 = sa; lam2 = sb; dl1 = da; dl2 = db; }
-      v0 = fmaf(p0, dac, v0); v1 = fmaf(p1, dac, v1); v2 = fmaf(p2, dac, v2);
-      v0 = fmaf(q0, dbc, v0); v1 = fmaf(q1, dbc, v1); v2 = fmaf(q2, dbc, v2);
-    }
-    // ---- residual: max over all rows of (impulse change x row diagonal)^2 ------------------------------------------
-    // With under-relaxed rows in the system the loop never meets Bullet's threshold (the oracle runs all iterations
-    // too): the global residual is only evaluated for models without them.
-    ++it;
-    if (it >= max_it) break;
-    const bool want_blk = blk_island && skip_mask == 0u;
-    if (self_mask == 0u || want_blk) {
-      const float r0 = dl0 * dg0, r1 = dl1 * dg1, r2 = dl2 * dg2;
-      const float rl = fmaxf(r0 * r0, fmaxf(r1 * r1, r2 * r2));
-      if (self_mask == 0u) {
-        const float resid = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rl)));   // rl >= 0: uint order = float order
-        if (resid <= thresh) break;
-      }
-      if (want_blk) {   // the island is frozen 100x below Bullet's threshold (3e-5 m/s of row velocity change)
-        const float rb = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(blk_lane ? rl : 0.f)));
-        if (rb <= 1e-2f * thresh) { skip_mask = blk_mask; active &= ~blk_mask; }
-      }
-    }
+  // The loop (macro: instantiated twice so that the common case carries no residual bookkeeping in its joint rows):
+  //   joint rows (motors, violated limits; swept backwards on even iterations)
+  //   contact normals, then friction cones, of the slots still swept (rolled loops over a bit mask: the body must stay
+  //     inside the L0 instruction cache)
+  //   residual: with under-relaxed rows in the system the loop never meets Bullet's threshold (the oracle runs all
+  //     iterations too), so the global residual is only evaluated for models without them (TRACKJ); the block island
+  //     is frozen 100x below Bullet's threshold (3e-5 m/s of row velocity change).
+#define BMI_PGS_LOOP(TRACKJ) \
+_Pragma("unroll 1") \
+  while (true) { \
+    if (it == n_c) kf = 1.f; \
+    BMI_JOINT_ROWS(true, TRACKJ); \
+_Pragma("unroll 1") \
+    for (unsigned m = active; m; m &= m - 1u) { \
+      const int c = __ffs(m) - 1; \
+      const unsigned a = ca + (unsigned)c * (3u * SS * 4u); \
+      const float c0 = lds_f(a), c1 = lds_f(a + 4u), c2 = lds_f(a + 8u); \
+      const float cand = fmaxf(fmaf(kf, fmaf(-v0, inv0, rhs0), lam0), 0.f); \
+      const float d = cand - lam0; \
+      const float dc = __shfl_sync(FULL, d, LANE_CT + c); \
+      if (myc == c) { lam0 = cand; dl0 = d; } \
+      v0 = fmaf(c0, dc, v0); v1 = fmaf(c1, dc, v1); v2 = fmaf(c2, dc, v2); \
+    } \
+_Pragma("unroll 1") \
+    for (unsigned m = active; m; m &= m - 1u) { \
+      const int c = __ffs(m) - 1; \
+      const unsigned a = ca + (unsigned)c * (3u * SS * 4u) + SS * 4u; \
+      const float p0 = lds_f(a), p1 = lds_f(a + 4u), p2 = lds_f(a + 8u); \
+      const float q0 = lds_f(a + SS * 4u), q1 = lds_f(a + SS * 4u + 4u), q2 = lds_f(a + SS * 4u + 8u); \
+      const float lim = mu * lam0; \
+      float sa = fmaf(kf, fmaf(-v1, inv1, rhs1), lam1), sb = fmaf(kf, fmaf(-v2, inv2, rhs2), lam2); \
+      const float n2 = sa * sa + sb * sb; \
+      const float sc = n2 > lim * lim ? lim * rsqrt_fast(n2) : 1.f; \
+      sa *= sc; sb *= sc; \
+      const float da = sa - lam1, db = sb - lam2; \
+      const float dac = __shfl_sync(FULL, da, LANE_CT + c), dbc = __shfl_sync(FULL, db, LANE_CT + c); \
+      if (myc == c) { lam1 = sa; lam2 = sb; dl1 = da; dl2 = db; } \
+      v0 = fmaf(p0, dac, v0); v1 = fmaf(p1, dac, v1); v2 = fmaf(p2, dac, v2); \
+      v0 = fmaf(q0, dbc, v0); v1 = fmaf(q1, dbc, v1); v2 = fmaf(q2, dbc, v2); \
+    } \
+    ++it; \
+    if (it >= max_it) break; \
+    const bool want_blk = blk_island && skip_mask == 0u; \
+    if (self_mask == 0u || want_blk) { \
+      const float r0 = dl0 * dg0, r1 = dl1 * dg1, r2 = dl2 * dg2; \
+      const float rl = fmaxf(r0 * r0, fmaxf(r1 * r1, r2 * r2)); \
+      if (self_mask == 0u) { \
+        const float resid = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(rl))); \
+        if (resid <= thresh) break; \
+      } \
+      if (want_blk) { \
+        const float rb = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(blk_lane ? rl : 0.f))); \
+        if (rb <= 1e-2f * thresh) { skip_mask = blk_mask; active &= ~blk_mask; } \
+      } \
+    } \
   }
+  if (self_mask != 0u) { BMI_PGS_LOOP(false); } else { BMI_PGS_LOOP(true); }
+#undef BMI_PGS_LOOP
 #undef BMI_JOINT_ROWS
 #undef BMI_LIMIT_ROWS
 #undef BMI_JOINT_EVENT

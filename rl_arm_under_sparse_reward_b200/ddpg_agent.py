@@ -300,14 +300,7 @@ class ddpg_agent:
                   float(a.clip_obs), float(a.clip_range), _lib.ptr(self.o_norm.mean_dev), _lib.ptr(self.o_norm.std_dev),
                   _lib.ptr(self.g_norm.mean_dev), _lib.ptr(self.g_norm.std_dev), _lib.ptr(self._x), _lib.ptr(self._xn),
                   _lib.ptr(self._a), _lib.ptr(self._r), st)
-        _lib.call("bmi_ddpg_backward", self._h, _lib.ptr(self._x), _lib.ptr(self._xn), _lib.ptr(self._a), _lib.ptr(self._r),
-                  _lib.ptr(self._losses), st)
-        if self._p2p:                # sync_grads of both nets (SUM, utils.py:43-48) fused into the Adam kernel over NVLink
-            _lib.call("bmi_ddpg_adam_step_p2p", self._h, st)
-            return
-        if utils.world_size() > 1:   # NCCL variant: both nets in ONE collective, then Adam
-            _lib.call("bmi_comm_allreduce_sum_f32", utils._state["comm"], self._grad_ptr, self._grad_n, st)
-        _lib.call("bmi_ddpg_adam_step", self._h, st)
+        self._learn_from(self._x, self._xn, self._a, self._r)
 
     def _update_network(self):
         """ddpg_agent.py:225-277, one update.  With device_rng=False the four HER arrays come from numpy's
@@ -333,10 +326,47 @@ class ddpg_agent:
             raise ValueError("cannot update from an empty replay buffer")
 
         def body():
-            for _ in range(n):
-                self._update_body()
+            self._sample_batches(n)
+            for i in range(n):
+                self._learn_from(self._XA[i], self._XNA[i], self._AA[i], self._RA[i])
         self._run_graphed(("update", n), body)
         self.updates += n
+
+    def _sample_batches(self, n):
+        """HER-sample ALL n batches of the cycle in ONE draw launch + ONE gather launch (n x batch_size transitions;
+        SURVEY 8d: a batch-256 gather is launch-bound).  Equivalent to n separate her.py:13-41 calls: the replay buffer
+        does not change between the updates of a cycle, the sampler does not depend on the networks, and the
+        counter-based Philox draws of sample k are the same whichever launch produces them."""
+        a, st, b = self.args, _lib.stream_ptr(), self.buffer
+        B = int(a.batch_size)
+        if getattr(self, "_XA", None) is None or self._XA.shape[0] != n:
+            f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
+            Dx = self.env_params['obs'] + self.env_params['goal']
+            self._XA, self._XNA, self._AA, self._RA = f32(n, B, Dx), f32(n, B, Dx), f32(n, B, self.env_params['action']), f32(n, B)
+            self._draw_all = (torch.zeros(n * B, dtype=torch.int64, device=self.device), torch.zeros(n * B, dtype=torch.int64, device=self.device),
+                              torch.zeros(n * B, dtype=torch.float64, device=self.device), torch.zeros(n * B, dtype=torch.float64, device=self.device))
+        bufs, d = b.buffers, self._draw_all
+        eps = _lib.Episodes(_lib.ptr(bufs['obs']), _lib.ptr(bufs['ag']), _lib.ptr(bufs['g']), _lib.ptr(bufs['actions']),
+                            b.size, b.T, bufs['obs'].shape[2], bufs['ag'].shape[2], bufs['actions'].shape[2],
+                            _lib.dtype_code(bufs['obs'].dtype), 0)
+        _lib.call("bmi_her_draw", ctypes.c_uint64(self._seed), _lib.ptr(self._ctr_her), n * B, _lib.ptr(b.current_size_dev),
+                  b.T, _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]), st)
+        _lib.call("bmi_her_sample_inputs", ctypes.byref(eps), -1, _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]),
+                  _lib.ptr(d[3]), n * B, float(self.her_module.future_p), float(self.her_module.distance_threshold),
+                  float(a.clip_obs), float(a.clip_range), _lib.ptr(self.o_norm.mean_dev), _lib.ptr(self.o_norm.std_dev),
+                  _lib.ptr(self.g_norm.mean_dev), _lib.ptr(self.g_norm.std_dev), _lib.ptr(self._XA), _lib.ptr(self._XNA),
+                  _lib.ptr(self._AA), _lib.ptr(self._RA), st)
+
+    def _learn_from(self, x, xn, act, r):
+        """ddpg_agent.py:250-277 on one prepared batch: 5 forward + 2 backward passes, gradient sum over ranks, Adam"""
+        st = _lib.stream_ptr()
+        _lib.call("bmi_ddpg_backward", self._h, _lib.ptr(x), _lib.ptr(xn), _lib.ptr(act), _lib.ptr(r), _lib.ptr(self._losses), st)
+        if self._p2p:                # sync_grads of both nets (SUM, utils.py:43-48) fused into the Adam kernel over NVLink
+            _lib.call("bmi_ddpg_adam_step_p2p", self._h, st)
+            return
+        if utils.world_size() > 1:   # NCCL variant: both nets in ONE collective, then Adam
+            _lib.call("bmi_comm_allreduce_sum_f32", utils._state["comm"], self._grad_ptr, self._grad_n, st)
+        _lib.call("bmi_ddpg_adam_step", self._h, st)
 
     def check_p2p(self):
         """utils.py:43-48 semantics must hold on every update: a timed-out peer-memory gradient sum is fatal (the kernel
