@@ -124,7 +124,7 @@ int bmi_her_sample_inputs(const bmi_episodes* buf, int64_t n_valid, const int64_
 /* Device-side draw of the four HER random arrays with a counter-based Philox4x32-10
  * generator (used when sampling happens inside a captured update graph, where numpy's
  * host stream is not available).  counter is read from *counter_dev and advanced by B so
- * replaying a graph yields fresh draws.  oracle/her_oracle.py restates the generator. */
+ * replaying a graph yields fresh draws.  oracle/philox.py + oracle/learner_oracle.py (her_draw_philox) restate the generator. */
 int bmi_her_draw(uint64_t seed, uint64_t* counter_dev, int64_t B, const int64_t* n_valid_dev,
                  int32_t T, int64_t* ep_idx_dev, int64_t* t_idx_dev, double* u_her_dev,
                  double* u_off_dev, bmi_stream_t stream);

@@ -9,7 +9,8 @@
 // Bit-exactness: every float64 operation that numpy performs is issued with the
 // round-to-nearest intrinsics (__dadd_rn/__dmul_rn/...) so nvcc cannot contract them
 // into FMAs; numpy's reduction order for a 3-vector norm is ((s0+s1)+s2) (verified
-// empirically, see tests/test_her_oracle.py).
+// against the unmodified reference: tests/test_oracle_learner.py::test_her_bit_exact_vs_reference and
+// tests/test_gpu_her.py::test_reward_kernel_matches_numpy).
 #include "common.cuh"
 
 namespace bmi {

@@ -466,7 +466,8 @@ __device__ __noinline__ void chol9(float* Lm, int lane) {
   const int row = lane < NL ? lane : NL - 1;
   float a[NL];
 #pragma unroll
-  for (int k = 0; k < NL; ++k) a[k] = Lm[row * NL + k];   // entries k > row are never used
+  for (int k = 0; k < NL; ++k) a[k] = lane < NL ? Lm[row * NL + k] : 0.f;   // entries k > row are never used; idle lanes must not
+                                                                            // read what lane 8 writes back below (racecheck)
 #pragma unroll
   for (int j = 0; j < NL; ++j) {
     const float pj = __shfl_sync(FULL, a[j], j);
@@ -1167,6 +1168,7 @@ _Pragma("unroll 1") \
 #undef BMI_LIMIT_ROWS
 #undef BMI_JOINT_EVENT
   PROF_CNT(s.prof_e, 7, it);
+  __syncwarp();   // the warm-start reads above are ordered before the stores below (shuffles are not memory barriers)
   {  // impulses of the block island for the next sub-step's warm start
     const int slot = __popc(blk_mask & ((1u << (myc & 31)) - 1u));   // rank of this lane's contact among the block-table contacts
     if (blk_island && blk_lane && slot < 4) { s.blk_lam[3 * slot] = lam0; s.blk_lam[3 * slot + 1] = lam1; s.blk_lam[3 * slot + 2] = lam2; }

@@ -12,7 +12,7 @@ from rl_arm_under_sparse_reward_b200.train import get_env_params
 a = Args(); a.add_demo, a.verbose, a.n_envs, a.buffer_size, a.save_dir, a.use_cuda_graphs = False, False, 64, 256 * 100, "/tmp/bmi_san/", False
 for task in ("push", "pick"):
     env = BmiVecEnv(64, task=task, seed=3)
-    p = get_env_params(env); p['max_timesteps'] = 3
+    p = get_env_params(env); p['max_timesteps'] = 2
     ag = ddpg_agent(a, env, p)
     ag.rollout(0)                                   # rollout_kernel (policy + IK + physics + record)
     env.reset(); env.step(torch.zeros(64, 4, device="cuda"))   # env_reset_kernel, env_step_kernel
@@ -24,6 +24,6 @@ for task in ("push", "pick"):
     print(task, "ok", ag.losses())
 PY
 for tool in memcheck racecheck; do
-  compute-sanitizer --tool $tool --print-limit 20 python /tmp/bmi_san.py > ${out}_$tool.log 2>&1
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/bmi_san.py > ${out}_$tool.log 2>&1
   echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' ${out}_$tool.log | tail -1)"
 done
