@@ -1093,9 +1093,10 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   do {                                                                                    \
     const bool fwd_ = !alternate || (it & 1);                                             \
     if (!fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, false, TRACK);                               \
+    int j = fwd_ ? 0 : NL - 1;                                                            \
+    const int jstep_ = fwd_ ? 1 : -1;                                                     \
     _Pragma("unroll (kMotorUnroll)")                                                      \
-    for (int jj = 0; jj < NL; ++jj) {                                                     \
-      const int j = fwd_ ? jj : NL - 1 - jj;                                              \
+    for (int jj = 0; jj < NL; ++jj, j += jstep_) {                                        \
       const float cand = fminf(fmaxf(lam0 + fmaf(-v0, inv0, rhs0), -max_imp), max_imp);   \
       const float d = cand - lam0;                                                        \
       const float dj = __shfl_sync(FULL, d, j);                                           \
@@ -1106,14 +1107,16 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   } while (0)
   unsigned active = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);   // contact slots still swept (bit c)
   float kf = n_c > 0 ? kself : 1.f;
-  // The loop (macro: instantiated twice so that the common case carries no residual bookkeeping in its joint rows):
+  // The loop (macro: three instances so that the common case carries no residual bookkeeping at all -- TRACKJ: joint rows
+  // record their last impulse change (models without under-relaxed rows: Bullet's residual exit); TRACKC: contact rows do
+  // (needed until the block island is frozen)):
   //   joint rows (motors, violated limits; swept backwards on even iterations)
   //   contact normals, then friction cones, of the slots still swept (rolled loops over a bit mask: the body must stay
   //     inside the L0 instruction cache)
   //   residual: with under-relaxed rows in the system the loop never meets Bullet's threshold (the oracle runs all
   //     iterations too), so the global residual is only evaluated for models without them (TRACKJ); the block island
   //     is frozen 100x below Bullet's threshold (3e-5 m/s of row velocity change).
-#define BMI_PGS_LOOP(TRACKJ) \
+#define BMI_PGS_LOOP(TRACKJ, TRACKC) \
 _Pragma("unroll 1") \
   while (true) { \
     if (it == n_c) kf = 1.f; \
@@ -1126,7 +1129,7 @@ _Pragma("unroll 1") \
       const float cand = fmaxf(fmaf(kf, fmaf(-v0, inv0, rhs0), lam0), 0.f); \
       const float d = cand - lam0; \
       const float dc = __shfl_sync(FULL, d, LANE_CT + c); \
-      if (myc == c) { lam0 = cand; dl0 = d; } \
+      if (myc == c) { lam0 = cand; if (TRACKC) dl0 = d; } \
       v0 = fmaf(c0, dc, v0); v1 = fmaf(c1, dc, v1); v2 = fmaf(c2, dc, v2); \
     } \
 _Pragma("unroll 1") \
@@ -1142,13 +1145,15 @@ _Pragma("unroll 1") \
       sa *= sc; sb *= sc; \
       const float da = sa - lam1, db = sb - lam2; \
       const float dac = __shfl_sync(FULL, da, LANE_CT + c), dbc = __shfl_sync(FULL, db, LANE_CT + c); \
-      if (myc == c) { lam1 = sa; lam2 = sb; dl1 = da; dl2 = db; } \
+      if (myc == c) { lam1 = sa; lam2 = sb; if (TRACKC) { dl1 = da; dl2 = db; } } \
       v0 = fmaf(p0, dac, v0); v1 = fmaf(p1, dac, v1); v2 = fmaf(p2, dac, v2); \
       v0 = fmaf(q0, dbc, v0); v1 = fmaf(q1, dbc, v1); v2 = fmaf(q2, dbc, v2); \
     } \
     ++it; \
     if (it >= max_it) break; \
+    if (!(TRACKC)) continue; \
     const bool want_blk = blk_island && skip_mask == 0u; \
+    if (!(TRACKJ) && !want_blk) break; \
     if (self_mask == 0u || want_blk) { \
       const float r0 = dl0 * dg0, r1 = dl1 * dg1, r2 = dl2 * dg2; \
       const float rl = fmaxf(r0 * r0, fmaxf(r1 * r1, r2 * r2)); \
@@ -1162,7 +1167,12 @@ _Pragma("unroll 1") \
       } \
     } \
   }
-  if (self_mask != 0u) { BMI_PGS_LOOP(false); } else { BMI_PGS_LOOP(true); }
+  if (self_mask != 0u) {
+    if (blk_island) { BMI_PGS_LOOP(false, true); }      // until the block island is frozen (2 sweeps on average) ...
+    if (it < max_it) { BMI_PGS_LOOP(false, false); }     // ... then without any residual bookkeeping
+  } else {
+    BMI_PGS_LOOP(true, true);
+  }
 #undef BMI_PGS_LOOP
 #undef BMI_JOINT_ROWS
 #undef BMI_LIMIT_ROWS

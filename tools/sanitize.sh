@@ -24,6 +24,6 @@ for task in ("push", "pick"):
     print(task, "ok", ag.losses())
 PY
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/bmi_san.py > ${out}_$tool.log 2>&1
+  timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/bmi_san.py > ${out}_$tool.log 2>&1
   echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' ${out}_$tool.log | tail -1)"
 done
