@@ -35,11 +35,12 @@ N_ENVS = 4096
 T = 100
 ALGO_BYTES_PER_ENV_STEP = 412          # state in+out 2x136 + action 16 + episode write 124
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_kernel launch (4096 envs x 100 steps), from the
-# `ncu --set full` capture summarised in profiles/r01_rollout_kernel_ncu.md (bench.py cannot run ncu itself)
-NCU_DRAM_BYTES_PER_LAUNCH = 80482304   # 4.774 MB read + 75.708 MB written
-# sm__warps_active / issue-slot utilisation / FMA pipe of the same capture (profiles/r02_rollout_kernel_ncu.md); numeric so
-# that the roofline object says what bounds this FP32-issue kernel (the HBM fraction cannot)
-NCU_ROLLOUT = {"warps_active_pct": None, "issue_slot_util_pct": None, "fma_pipe_pct": None}
+# `ncu --set full` capture summarised in profiles/r02_rollout_kernel_ncu.md (bench.py cannot run ncu itself)
+NCU_DRAM_BYTES_PER_LAUNCH = 108596736  # 17.92 MB read + 90.68 MB written
+# sm__warps_active / smsp__issue_active / FMA pipe of the same capture; numeric so that the roofline object says what bounds
+# this FP32-issue kernel (the HBM fraction cannot): 28 of 64 warp slots resident by design (shared memory), issue slots 75 % busy
+NCU_ROLLOUT = {"warps_active_pct": 42.2, "issue_slot_util_pct": 75.3, "fma_pipe_pct": 28.6, "lsu_pipe_pct": 60.6,
+               "warp_instructions_per_env_substep": 36600}
 METRIC = "env-steps/s (push, 4096 envs) at 1/2/4/8 B200 vs CPU PyBullet+MPI"
 
 
@@ -235,7 +236,9 @@ def run_replay_stress(args):
     if world == 1:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
-    E = 5000
+    if os.environ.get("BMI_L2_FETCH"):       # experiment knob: DRAM bytes fetched per L2 miss (32 / 64 / 128)
+        _lib.call("bmi_set_l2_fetch_granularity", int(os.environ["BMI_L2_FETCH"]))
+    E = args.stress_episodes
     g = torch.Generator(device=dev).manual_seed(125 + rank)
     obs = torch.randn(E, T + 1, 27, device=dev, generator=g)
     ag = 0.3 + 0.1 * torch.randn(E, T + 1, 3, device=dev, generator=g)
@@ -293,7 +296,7 @@ def run_replay_stress(args):
                 "value": top["transitions_per_s"], "unit": "transitions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": top["us"] * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "replay-stress: 5000 episodes x 100 steps of N(0,1) obs / N(0.3,0.1) goals / U(-0.5,0.5) actions per GPU, "
+                "config": {"workload": "replay-stress: %d episodes x 100 steps" % E + " of N(0,1) obs / N(0.3,0.1) goals / U(-0.5,0.5) actions per GPU, "
                                        "her_inputs_kernel batch sweep, value = batch %d" % top["batch"],
                            "l2": "flushed before every timed launch (256 MiB fill); the 75 MB float32 buffer itself fits the 126 MB L2",
                            "parallelism": "dp%d (one buffer per rank, no data-path collective)" % world},
@@ -521,7 +524,8 @@ def run_gpu(args):
                              "kernel": kernel_name, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * a.n_envs * T,
                              "kernel_ms": kern_ms, "kernel_share_of_step": kernel_share, "peak_source": peak_src,
                              "warps_active_pct": NCU_ROLLOUT["warps_active_pct"], "issue_slot_util_pct": NCU_ROLLOUT["issue_slot_util_pct"],
-                             "fma_pipe_pct": NCU_ROLLOUT["fma_pipe_pct"],
+                             "fma_pipe_pct": NCU_ROLLOUT["fma_pipe_pct"], "lsu_pipe_pct": NCU_ROLLOUT["lsu_pipe_pct"],
+                             "warp_instructions_per_env_substep": NCU_ROLLOUT["warp_instructions_per_env_substep"],
                              "note": "FP32-issue bound kernel (SURVEY 8d): the HBM fraction is small by construction; what bounds it is the issue-slot "
                                      "utilisation above (ncu capture in profiles/)"},
                 "cpu_baseline": cpu, "e2e": e2e, "e2e_async": e2e_async, "multi_rank": multi,
@@ -546,6 +550,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-probe", action="store_true", help="skip the multi-rank parity probe")
+    ap.add_argument("--stress-episodes", type=int, default=5000, help="replay-stress: stored episodes per GPU (5000 = 5e5 transitions)")
     ap.add_argument("--stepwise", action="store_true", help="step-wise rollout pipeline instead of the fused kernel")
     args = ap.parse_args()
     if args.impl == "reference":

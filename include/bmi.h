@@ -46,6 +46,8 @@ int bmi_abi_version(void);
 const char* bmi_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py: gpu_launches) */
 int64_t bmi_launch_count(void);
+/* hint: bytes fetched from DRAM per L2 miss (32 / 64 / 128) for the random gathers of the path (her.py:24-36 fancy indexing) */
+int bmi_set_l2_fetch_granularity(int32_t bytes);
 
 /* ------------------------------------------------------------------------------------
  * Episode store (struct-of-arrays by key, episode-major inside each key) — the layout of

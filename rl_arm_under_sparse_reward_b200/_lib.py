@@ -55,6 +55,7 @@ SIGNATURES = {
     "bmi_abi_version": (c_int32, []),
     "bmi_last_error": (c_char_p, []),
     "bmi_launch_count": (c_int64, []),
+    "bmi_set_l2_fetch_granularity": (c_int32, [c_int32]),
     "bmi_buffer_store": (c_int32, [POINTER(Episodes), POINTER(Episodes), c_void_p, c_void_p]),
     "bmi_compute_reward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_double,
                                      c_void_p, c_void_p]),
