@@ -11,6 +11,9 @@
 // into FMAs; numpy's reduction order for a 3-vector norm is ((s0+s1)+s2) (verified
 // against the unmodified reference: tests/test_oracle_learner.py::test_her_bit_exact_vs_reference and
 // tests/test_gpu_her.py::test_reward_kernel_matches_numpy).
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 
 namespace bmi {
@@ -233,6 +236,145 @@ her_inputs_kernel(bmi_episodes buf, const int64_t* __restrict__ ep_idx,
   }
 }
 
+// (c - m) / sd rounded to float64 exactly like __ddiv_rn, at the price of one multiplication: q~ = d * (1 / sd) is
+// within 3 units of the correctly rounded quotient, so after the float32 cast the two can only differ when q~ lies
+// within a few units of a float32 rounding boundary (low 29 mantissa bits == 0x10000000), of the float32 subnormal
+// range or of a non-finite value -- those rare lanes take the exact division.
+__device__ __noinline__ double ddiv_exact(double d, double sd) { return __ddiv_rn(d, sd); }
+__device__ __forceinline__ double div_as_f32_exact(double d, double sd, double rsd) {
+  double q = __dmul_rn(d, rsd);
+  const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu;
+  const unsigned hi = (unsigned)__double2hiint(q) & 0x7FF00000u;
+  const bool risky = (lo - 0x0FFFFFF8u) <= 16u || ((hi - 0x38400000u) >= 0x44C00000u && d != 0.0);   // 2^-123 <= |q| < 2^977
+  if (risky) q = ddiv_exact(d, sd);
+  return q;
+}
+
+// clip -> normalise -> clip -> float32 of one stored value (ddpg_agent.py:229-248 with normalizer.py:66-70).  F32CLIP: both
+// clip limits are float32-representable, so the outer clip commutes with the (monotonic) float32 rounding and, for float32
+// storage, the inner one can run before the widening -- single FMNMX instructions instead of float64 compare / select pairs.
+template <typename T, bool F32CLIP>
+__device__ __forceinline__ float norm_clip_lane(T v, double clip_obs, double m, double sd, double rsd, double clip_range) {
+  double c;
+  if (F32CLIP && sizeof(T) == 4) {
+    const float lim = (float)clip_obs;
+    c = (double)fminf(fmaxf((float)v, -lim), lim);
+  } else {
+    c = clipd((double)v, clip_obs);
+  }
+  const double q = div_as_f32_exact(__dsub_rn(c, m), sd, rsd);
+  if (F32CLIP) {
+    const float lim = (float)clip_range;
+    return fminf(fmaxf((float)q, -lim), lim);
+  }
+  return (float)clipd(q, clip_range);
+}
+
+// Lane-per-element sampler for the common narrow layouts (obs_dim + goal_dim <= 32, act_dim <= 32, < 2^32 stored rows): a
+// warp handles HER_S sampled transitions at a time and lane i owns column i of the network input -- lanes [0, Do) the
+// observation pair (two loads, rows t and t + 1), lanes [Do, Do + Dg) the (relabelled) goal and ag_next, lanes [0, Da)
+// also the action.  The sampled rows of a 16-sample chunk are resolved one per lane (coalesced index loads) and broadcast
+// with shuffles; all loads of HER_S samples are issued before the first use; both input rows leave as one coalesced
+// 4 * Dx-byte store each.  A persistent grid (8 blocks per SM) amortises the per-lane constants (mean, std, 1 / std).
+// sq_thr is the largest float64 whose correctly rounded square root is <= thr, so "sqrt(acc) > thr" is "acc > sq_thr".
+// Results identical bit for bit to the float64-division chain.
+// HER_CH: samples per warp chunk, their (episode, t, future t) rows resolved one per lane; HER_S: samples whose loads are in
+// flight together.  16 / 8 for bandwidth-bound batches; 4 / 4 for launch-bound ones (a warp's chunk is then ONE memory round
+// trip and a batch of 256 still spreads over 64 warps).  DG: goal_dim known at compile time (0: use buf.goal_dim)
+template <typename T, bool F32CLIP, int DG, int HER_CH, int HER_S>
+__global__ void __launch_bounds__(128, 8)
+her_inputs_lane_kernel(bmi_episodes buf, const int64_t* __restrict__ ep_idx, const int64_t* __restrict__ t_idx,
+                       const double* __restrict__ u_her, const double* __restrict__ u_off, int64_t B, double future_p,
+                       double sq_thr, double clip_obs, double clip_range, const float* __restrict__ o_mean,
+                       const float* __restrict__ o_std, const float* __restrict__ g_mean,
+                       const float* __restrict__ g_std, float* __restrict__ x, float* __restrict__ xn,
+                       float* __restrict__ actions, float* __restrict__ rew) {
+  const int lane = threadIdx.x & 31;
+  const unsigned Tn = buf.T, Do = buf.obs_dim, Dg = DG ? DG : buf.goal_dim, Da = buf.act_dim, Dx = Do + Dg;
+  const bool is_obs = lane < Do, is_goal = !is_obs && lane < Dx;
+  const int kg = lane - Do;
+  double m = 0.0, sd = 1.0;
+  if (is_obs) { m = (double)o_mean[lane]; sd = (double)o_std[lane]; }
+  if (is_goal) { m = (double)g_mean[kg]; sd = (double)g_std[kg]; }
+  const double rsd = __ddiv_rn(1.0, sd);
+  // per-lane address recipe: value A = baseA[idxA * strideA], value B = baseB[(row + 1) * strideA]
+  const T* const agk = (const T*)buf.ag + (is_goal ? kg : 0);
+  const T* const gk = (const T*)buf.g + (is_goal ? kg : 0);
+  const T* const obl = (const T*)buf.obs + (is_obs ? lane : 0);
+  const T* const baseB = is_goal ? agk : obl;
+  const unsigned strideA = is_goal ? Dg : Do;
+  const unsigned Bu = (unsigned)B;                        // the host guarantees B * max(Dx, Da) < 2^32
+  const unsigned n_chunks = (Bu + HER_CH - 1) / HER_CH;
+  const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned chunk = warp0; chunk < n_chunks; chunk += n_warps) {
+    const unsigned c0 = chunk * HER_CH;
+    // ---- lane l resolves sample c0 + (l mod HER_CH); the tail repeats the last sample (not stored) --------------------
+    unsigned l_row, l_tr, l_goal, her_mask;
+    {
+      const unsigned b = min(c0 + (lane & (HER_CH - 1)), Bu - 1u);
+      const unsigned ep = (unsigned)ep_idx[b], t = (unsigned)t_idx[b];
+      const bool her = u_her[b] < future_p;                                                                  // her.py:28
+      const unsigned ft = t + 1u + (unsigned)__double2int_rz(__dmul_rn(u_off[b], (double)(int)(Tn - t)));    // her.py:30-32
+      l_row = ep * (Tn + 1u) + t;
+      l_tr = ep * Tn + t;
+      l_goal = her ? l_row - t + ft : l_tr;     // row of ag (relabelled) or of g (stored goal)
+      her_mask = __ballot_sync(0xffffffffu, her);
+    }
+    // ---- actions of the whole chunk: element j = (sample, component) -----------------------------------------------------
+    for (unsigned j0 = 0; j0 < HER_CH * Da; j0 += 32) {      // uniform trip count: the shuffle needs every lane
+      const unsigned j = j0 + lane;
+      const bool valid = j < HER_CH * Da;
+      const unsigned sI = valid ? j / Da : 0u, k = j - sI * Da;
+      const unsigned tr = __shfl_sync(0xffffffffu, l_tr, sI);
+      if (valid && c0 + sI < Bu) actions[(c0 + sI) * Da + k] = (float)((const T*)buf.actions)[(uint64_t)tr * Da + k];
+    }
+#pragma unroll
+    for (int h = 0; h < HER_CH / HER_S; ++h) {
+      T va[HER_S], vb[HER_S];
+#pragma unroll
+      for (int s = 0; s < HER_S; ++s) {
+        const int src = h * HER_S + s;
+        const unsigned row = __shfl_sync(0xffffffffu, l_row, src);
+        const unsigned gl = __shfl_sync(0xffffffffu, l_goal, src);
+        const bool her = (her_mask >> src) & 1u;
+        const T* baseA = is_goal ? (her ? agk : gk) : obl;
+        va[s] = baseA[(uint64_t)(is_goal ? gl : row) * strideA];
+        vb[s] = baseB[(uint64_t)(row + 1u) * strideA];
+      }
+#pragma unroll
+      for (int s = 0; s < HER_S; ++s) {
+        const unsigned b = c0 + h * HER_S + s;
+        const float xa = norm_clip_lane<T, F32CLIP>(va[s], clip_obs, m, sd, rsd, clip_range);
+        float xb = xa;                                    // g_next is the same relabelled goal (ddpg_agent.py:231)
+        if (is_obs) xb = norm_clip_lane<T, F32CLIP>(vb[s], clip_obs, m, sd, rsd, clip_range);
+        // reward: numpy order ((d0^2 + d1^2) + d2^2) (bmirobot_env_push_F.py:84-90)
+        const double d = __dsub_rn((double)vb[s], (double)va[s]);
+        const double sq = __dmul_rn(d, d);
+        double acc = __shfl_sync(0xffffffffu, sq, Do);
+#pragma unroll
+        for (unsigned k = 1; k < Dg; ++k) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, sq, Do + k));
+        if (b < Bu) {
+          if (lane < Dx) {
+            x[b * Dx + lane] = xa;
+            xn[b * Dx + lane] = xb;
+          }
+          if (lane == 0) rew[b] = (acc > sq_thr) ? -1.0f : -0.0f;
+        }
+      }
+    }
+  }
+}
+
+// largest float64 a with sqrt_rn(a) <= thr (sqrt_rn is monotonic, the host's sqrt is correctly rounded)
+static double sqrt_threshold(double thr) {
+  if (!(thr >= 0.0)) return -1.0;                 // sqrt(acc) >= 0 > thr for every acc (NaN thr: comparison false anyway)
+  double a = thr * thr;
+  while (std::sqrt(a) <= thr) a = std::nextafter(a, INFINITY);
+  while (std::sqrt(a) > thr) a = std::nextafter(a, -INFINITY);
+  return a;
+}
+
 // ---- device-side draws -------------------------------------------------------------------
 __global__ void her_draw_kernel(uint64_t seed, const uint64_t* __restrict__ counter, int64_t B,
                                 const int64_t* __restrict__ n_valid_p, int T,
@@ -376,11 +518,33 @@ extern "C" int bmi_her_sample_inputs(const bmi_episodes* buf, int64_t n_valid,
   her_inputs_kernel<TT, TILE><<<(unsigned)((B + (TILE) - 1) / (TILE)), HER_THREADS, 0, as_stream(stream)>>>(        \
       *buf, ep_idx, t_idx, u_her, u_off, B, future_p, thr, clip_obs, clip_range, o_mean, o_std, g_mean, g_std, x, \
       xn, actions, r)
-  if (buf->dtype == BMI_F64) {
+#define BMI_HER_LANE(TT, FC)                                                                                  \
+  { if (buf->goal_dim == 3) BMI_HER_LANE_(TT, FC, 3) else BMI_HER_LANE_(TT, FC, 0) }
+#define BMI_HER_LANE_(TT, FC, DG)                                                                             \
+  { if (B > 16384) { BMI_HER_LANE__(TT, FC, DG, 16, 8); } else { BMI_HER_LANE__(TT, FC, DG, 4, 4); } }
+#define BMI_HER_LANE__(TT, FC, DG, CH, S)                                                                     \
+  her_inputs_lane_kernel<TT, FC, DG, CH, S><<<lane_grid, 128, 0, as_stream(stream)>>>(                                    \
+      *buf, ep_idx, t_idx, u_her, u_off, B, future_p, sq_thr, clip_obs, clip_range, o_mean, o_std, g_mean, g_std, x, \
+      xn, actions, r)
+  const bool narrow = buf->obs_dim + buf->goal_dim <= 32 &&     // act_dim <= 32 is checked by check_eps
+                      (double)buf->n_episodes * (buf->T + 1) < 4294967296.0 && (double)B * 32.0 < 4294967296.0 &&
+                      std::isfinite(thr);
+  if (narrow) {
+    const int64_t her_ch = B > 16384 ? 16 : 4;
+    const int64_t n_chunks = (B + her_ch - 1) / her_ch;
+    const unsigned lane_grid = (unsigned)std::min<int64_t>((n_chunks + 3) / 4, 148 * 8);
+    const double sq_thr = sqrt_threshold(thr);
+    const bool fc = (double)(float)clip_obs == clip_obs && (double)(float)clip_range == clip_range;
+    if (buf->dtype == BMI_F64) { if (fc) { BMI_HER_LANE(double, true); } else { BMI_HER_LANE(double, false); } }
+    else { if (fc) { BMI_HER_LANE(float, true); } else { BMI_HER_LANE(float, false); } }
+  } else if (buf->dtype == BMI_F64) {
     if (B <= 8192) BMI_HER_LAUNCH(double, 8); else BMI_HER_LAUNCH(double, 64);
   } else {
     if (B <= 8192) BMI_HER_LAUNCH(float, 8); else BMI_HER_LAUNCH(float, 64);
   }
+#undef BMI_HER_LANE
+#undef BMI_HER_LANE_
+#undef BMI_HER_LANE__
 #undef BMI_HER_LAUNCH
   BMI_LAUNCHED();
   return BMI_OK;

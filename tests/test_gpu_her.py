@@ -168,6 +168,43 @@ def test_fused_network_inputs_bit_exact(golden_dir):
         assert np.array_equal(A.cpu().numpy(), a) and np.array_equal(Rr.cpu().numpy(), r[:, 0])
 
 
+def test_fused_inputs_large_ragged_batch_bit_exact():
+    """The lane-per-element sampler (multiplication by 1 / std with an exact-division slow path) == numpy float64 division,
+    on 100 003 samples (ragged tail) of a random buffer, both storage dtypes; a few values sit exactly on float32 rounding
+    boundaries so that the slow path runs."""
+    _lib, _, _ = _mods()
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(11)
+    E, T, B = 300, 100, 100003
+    buf = {"obs": rng.standard_normal((E, T + 1, 27)) * 0.7, "ag": 0.3 + rng.standard_normal((E, T + 1, 3)) * 0.03,
+           "g": 0.3 + rng.standard_normal((E, T, 3)) * 0.03, "actions": rng.uniform(-0.5, 0.5, (E, T, 4))}
+    on, gn = lo.Normalizer(27, clip=5), lo.Normalizer(3, clip=5)
+    on.mean, on.std = (rng.standard_normal(27) * 0.2).astype(np.float32), rng.uniform(0.05, 1.5, 27).astype(np.float32)
+    gn.mean, gn.std = (0.3 + rng.standard_normal(3) * 0.01).astype(np.float32), rng.uniform(0.01, 0.1, 3).astype(np.float32)
+    on.mean[5], on.std[5] = 0.0, 1.0
+    buf["obs"][:, :, 5] = 1.0 + 2.0 ** -24 * rng.randint(-3, 4, (E, T + 1))        # float32 midpoints / representable values
+    buf["obs"][:, ::7, 6] = on.mean[6]                                              # exact zeros after the subtraction
+    np.random.seed(9)
+    draws = lo.her_draw_numpy(E, T, B)
+    for dt in (torch.float64, torch.float32):
+        src = buf if dt == torch.float64 else {k: v.astype(np.float32).astype(np.float64) for k, v in buf.items()}
+        x, xn, a, r = lo.network_inputs(lo.her_sample_with_draws(src, draws, 0.8), on, gn)
+        t = {k: torch.as_tensor(v).to(dev, dt).contiguous() for k, v in buf.items()}
+        eps = _lib.Episodes(_lib.ptr(t["obs"]), _lib.ptr(t["ag"]), _lib.ptr(t["g"]), _lib.ptr(t["actions"]), E, T, 27, 3, 4,
+                            _lib.dtype_code(dt), 0)
+        d = [torch.as_tensor(v).to(dev) for v in draws]
+        mk = lambda *s: torch.full(s, 7.0, dtype=torch.float32, device=dev)
+        X, XN, A, Rr = mk(B + 4, 30), mk(B + 4, 30), mk(B + 4, 4), mk(B + 4)
+        st = [torch.as_tensor(v).to(dev) for v in (on.mean, on.std, gn.mean, gn.std)]
+        _lib.call("bmi_her_sample_inputs", ctypes.byref(eps), E, _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]),
+                  B, 0.8, 0.05, 200.0, 5.0, _lib.ptr(st[0]), _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]), _lib.ptr(X),
+                  _lib.ptr(XN), _lib.ptr(A), _lib.ptr(Rr), _lib.stream_ptr())
+        assert np.array_equal(X[:B].cpu().numpy(), x) and np.array_equal(XN[:B].cpu().numpy(), xn)
+        assert np.array_equal(A[:B].cpu().numpy(), a) and np.array_equal(Rr[:B].cpu().numpy(), r[:, 0])
+        for tail in (X, XN, A, Rr):                                                  # nothing written past the batch
+            assert bool((tail[B:] == 7.0).all())
+
+
 def test_device_philox_draws_match_oracle():
     _lib, _, _ = _mods()
     dev = torch.device("cuda")
