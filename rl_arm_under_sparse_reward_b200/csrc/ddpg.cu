@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ddpg_fused.cuh"
 
 namespace bmi {
 
@@ -97,6 +98,9 @@ struct bmi_ddpg {
   float *qh1 = nullptr, *qh2 = nullptr, *qh3 = nullptr, *qa = nullptr, *xca = nullptr; // critic(x, pi(x))
   float *a_next = nullptr, *q_next = nullptr, *y = nullptr;
   float *d1 = nullptr, *d2 = nullptr, *dq = nullptr, *dq_const = nullptr, *dxc = nullptr, *dz = nullptr;    // backward scratch
+  // hand-written two-launch update (ddpg_fused.cuh): chosen at creation when the shapes fit (hidden 256, ...)
+  bool fused = false;
+  float *cd1 = nullptr, *cd2 = nullptr, *cd3 = nullptr, *fd1 = nullptr, *fd2 = nullptr, *fd3 = nullptr, *loss_part = nullptr;
   float* bg_part = nullptr;        // drelu_bgrad: partial column sums [row chunks][hidden]
   unsigned* bg_ticket = nullptr;   // ... and one ticket counter per 32-column group
   // policy (act) activations (max_act_rows)
@@ -607,6 +611,15 @@ extern "C" int bmi_ddpg_create(bmi_ddpg** out, const bmi_ddpg_config* cfg, float
   A_(d1, B * H); A_(d2, B * H); A_(dq, B > H ? B : H); A_(dq_const, B); A_(bg_part, (size_t)((B + 31) / 32) * H); A_(dxc, B * (Dx + Da)); A_(dz, B * Da > H ? B * Da : H);
   A_(ph1, (size_t)cfg->max_act_rows * H); A_(ph2, (size_t)cfg->max_act_rows * H);
   A_(pz, (size_t)cfg->max_act_rows * Da);
+  // BMI_DDPG_CUBLAS=1 keeps the cuBLASLt chain (A/B measurements, tests of both paths)
+  const char* force_lt = getenv("BMI_DDPG_CUBLAS");
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+  h->fused = !(force_lt && force_lt[0] == '1') && H == FH && B % 32 == 0 && Dx + Da <= FIN && Da <= FOUT && al16(actor) &&
+             al16(critic) && al16(actor_t) && al16(critic_t);
+  if (h->fused) {
+    A_(cd1, B * H); A_(cd2, B * H); A_(cd3, B * H); A_(fd1, B * H); A_(fd2, B * H); A_(fd3, B * H);
+    A_(loss_part, (size_t)(B / FR) * 4);
+  }
 #undef A_
   if (!rc) {
     void* p = nullptr;
@@ -694,6 +707,47 @@ extern "C" int bmi_ddpg_backward(bmi_ddpg* h, const float* x, const float* xn, c
   float* Ga = h->grads;
   float* Gc = h->grads + h->na_pad;
   int rc;
+  if (h->fused) {
+    FusedArgs fa;
+    fa.P[0] = h->actor; fa.P[1] = h->critic; fa.P[2] = h->actor_t; fa.P[3] = h->critic_t;
+    for (int l = 0; l < 4; ++l) {
+      fa.wa[l] = (int)h->la.w[l]; fa.ba[l] = (int)h->la.b[l];
+      fa.wc[l] = (int)h->lc.w[l]; fa.bc[l] = (int)h->lc.b[l];
+    }
+    fa.x = x; fa.xn = xn; fa.act = actions; fa.r = r;
+    fa.xc = h->xc; fa.ch1 = h->ch1; fa.ch2 = h->ch2; fa.ch3 = h->ch3;
+    fa.cd1 = h->cd1; fa.cd2 = h->cd2; fa.cd3 = h->cd3; fa.dq = h->dq;
+    fa.ah1 = h->ah1; fa.ah2 = h->ah2; fa.ah3 = h->ah3;
+    fa.fd1 = h->fd1; fa.fd2 = h->fd2; fa.fd3 = h->fd3; fa.dz = h->dz;
+    fa.loss_part = h->loss_part;
+    fa.B = B; fa.Dx = Dx; fa.Da = Da;
+    fa.amax = amax; fa.gamma = c.gamma; fa.clip_ret = c.clip_return; fa.l2 = c.action_l2;
+    ddpg_rows_kernel<<<B / FR, FT, 0, st>>>(fa);
+    BMI_LAUNCHED();
+    WgradArgs wg;
+    const int H = c.hidden;
+    //            critic W4      W3       W2       W1       actor W4   W3       W2       W1
+    const float* Dp[WG_P] = {h->dq, h->cd3, h->cd2, h->cd1, h->dz, h->fd3, h->fd2, h->fd1};
+    const float* Ap[WG_P] = {h->ch3, h->ch2, h->ch1, h->xc, h->ah3, h->ah2, h->ah1, x};
+    const int ldD[WG_P] = {1, H, H, H, Da, H, H, H}, ldA[WG_P] = {H, H, H, Dc, H, H, H, Dx};
+    const int Nj[WG_P] = {1, H, H, H, Da, H, H, H}, Nk[WG_P] = {H, H, H, Dc, H, H, H, Dx};
+    float* gWp[WG_P] = {Gc + h->lc.w[3], Gc + h->lc.w[2], Gc + h->lc.w[1], Gc + h->lc.w[0],
+                        Ga + h->la.w[3], Ga + h->la.w[2], Ga + h->la.w[1], Ga + h->la.w[0]};
+    float* gbp[WG_P] = {Gc + h->lc.b[3], Gc + h->lc.b[2], Gc + h->lc.b[1], Gc + h->lc.b[0],
+                        Ga + h->la.b[3], Ga + h->la.b[2], Ga + h->la.b[1], Ga + h->la.b[0]};
+    int tiles = 0;
+    for (int p = 0; p < WG_P; ++p) {
+      wg.D[p] = Dp[p]; wg.Ac[p] = Ap[p]; wg.gW[p] = gWp[p]; wg.gb[p] = gbp[p];
+      wg.ldD[p] = ldD[p]; wg.ldA[p] = ldA[p]; wg.Nj[p] = Nj[p]; wg.Nk[p] = Nk[p];
+      wg.tile0[p] = tiles;
+      tiles += ((Nj[p] + WG_TJ - 1) / WG_TJ) * ((Nk[p] + WG_TK - 1) / WG_TK);
+    }
+    wg.tile0[WG_P] = tiles;
+    wg.loss_part = h->loss_part; wg.losses = losses; wg.n_part = B / FR; wg.B = B; wg.Da = Da; wg.l2 = c.action_l2;
+    ddpg_wgrad_kernel<<<tiles, 256, 0, st>>>(wg);
+    BMI_LAUNCHED();
+    return BMI_OK;
+  }
   // ---- target: y = clamp(r + gamma * Q'(x', pi'(x')), -1/(1-gamma), 0) -------------------
   if ((rc = mlp_hidden(h, st, h->la, h->actor_t, xn, B, h->h1, h->h2, h->h3))) return rc;
   if ((rc = mlp_out(h, st, h->la, h->actor_t, h->h3, B, h->az))) return rc;

@@ -113,6 +113,29 @@ def test_losses_and_gradients_vs_torch_oracle():
     T.close()
 
 
+def test_fused_update_matches_cublaslt_chain(monkeypatch):
+    """The hand-written two-launch update (ddpg_fused.cuh, the default at hidden = 256) against the cuBLASLt chain
+    (BMI_DDPG_CUBLAS=1) on the same batch: same gradients and losses up to fp32 summation order, and 2 launches instead of ~54."""
+    L = _seeded(21)
+    x, xn, a, r = _batch(3)
+    out = {}
+    for name, flag in (("fused", "0"), ("lt", "1")):
+        monkeypatch.setenv("BMI_DDPG_CUBLAS", flag)
+        T = Trainer(L)
+        T.backward(x, xn, a, r)                    # first call of the cuBLASLt path builds its plans
+        n0 = T._lib.launch_count()
+        T.backward(x, xn, a, r)
+        out[name] = (T.losses.cpu().numpy().copy(), T.grads(), T._lib.launch_count() - n0)
+        T.close()
+    assert out["fused"][2] == 2 and out["lt"][2] > 40, (out["fused"][2], out["lt"][2])
+    assert np.allclose(out["fused"][0], out["lt"][0], rtol=1e-5, atol=1e-7)
+    for mine, ref in zip(out["fused"][1][:2], out["lt"][1][:2]):
+        scale = np.abs(ref).max()
+        assert np.abs(mine - ref).max() <= 1e-4 * scale + 1e-9, np.abs(mine - ref).max() / scale
+        assert np.linalg.norm(mine - ref) <= 2e-5 * np.linalg.norm(ref)
+    assert np.all(out["fused"][1][2] == 0)
+
+
 def test_actor_forward_matches_torch():
     L = _seeded(5)
     T = Trainer(L, max_rows=4096)
