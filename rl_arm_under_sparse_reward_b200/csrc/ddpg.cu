@@ -86,7 +86,7 @@ struct bmi_ddpg {
   int64_t na_pad = 0, n_grads = 0;
   float *adam_m = nullptr, *adam_v = nullptr;   // same layout as grads
   int* adam_step = nullptr;                     // device step counter
-  float* adam_scal = nullptr;                   // [4] step_size_a, step_size_c, 1/sqrt(bc2), -
+  float* adam_scal = nullptr;                   // two slots of [step_size_a, step_size_c, sqrt(bc2), -]: slot (t & 1) for step t
   cublasLtHandle_t lt = nullptr;
   void* workspace = nullptr;
   size_t workspace_bytes = 8u << 20;
@@ -103,6 +103,7 @@ struct bmi_ddpg {
   float *cd1 = nullptr, *cd2 = nullptr, *cd3 = nullptr, *fd1 = nullptr, *fd2 = nullptr, *fd3 = nullptr, *loss_part = nullptr;
   float* bg_part = nullptr;        // drelu_bgrad: partial column sums [row chunks][hidden]
   unsigned* bg_ticket = nullptr;   // ... and one ticket counter per 32-column group
+  unsigned* adam_ticket = nullptr; // adam_kernel: blocks finished (the last one advances the step counter)
   // policy (act) activations (max_act_rows)
   float *ph1 = nullptr, *ph2 = nullptr, *pz = nullptr;
   std::vector<void*> owned;
@@ -356,10 +357,14 @@ __global__ void bgrad_kernel(const float* __restrict__ dZ, int rows, int cols, f
   }
 }
 
-__global__ void adam_prepare_kernel(int* step, float* scal, float lr_a, float lr_c, float b1, float b2) {
-  int t = ++(*step);
-  double bc1 = 1.0 - pow((double)b1, (double)t);
-  double bc2 = 1.0 - pow((double)b2, (double)t);
+// bias-corrected step sizes of optimiser step t, as torch computes them (python doubles, then float32): scal[0..2].
+// No separate one-thread launch: the scalars live in a two-slot ring (slot t & 1 for step t).  The launch of step t reads its
+// slot -- written by the launch of step t - 1, or by the host for t = 1 -- while ONE thread of the grid evaluates the two
+// pow() calls for step t + 1 off the critical path (about 4 us, as long as the whole Adam pass).  The step counter is advanced
+// by the LAST block to finish (adam_kernel: ticket; adam_p2p_kernel: its "done" section), after every block has read it.
+__host__ __device__ inline void adam_scalars(int t, float lr_a, float lr_c, float b1, float b2, float* scal) {
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
   scal[0] = (float)((double)lr_a / bc1);
   scal[1] = (float)((double)lr_c / bc1);
   scal[2] = (float)sqrt(bc2);
@@ -368,18 +373,33 @@ __global__ void adam_prepare_kernel(int* step, float* scal, float lr_a, float lr
 // torch.optim.Adam (_single_tensor_adam) on the concatenated [actor | critic] buffers
 __global__ void adam_kernel(float* __restrict__ pa, float* __restrict__ pc, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, int64_t na, int64_t na_pad,
-                            int64_t n, const float* __restrict__ scal, float b1, float b2, float eps) {
+                            int64_t n, int* step_ctr, unsigned* ticket, float* scal_ring, float lr_a, float lr_c, float b1,
+                            float b2, float eps) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || (i >= na && i < na_pad)) return;
-  float gi = g[i];
-  float mi = m[i] + (gi - m[i]) * (1.0f - b1);          // exp_avg.lerp_(grad, 1-beta1)
-  float vi = v[i] * b2 + (1.0f - b2) * gi * gi;         // mul_(beta2).addcmul_(g, g, 1-beta2)
-  m[i] = mi;
-  v[i] = vi;
-  float denom = sqrtf(vi) / scal[2] + eps;
-  float step = i < na ? scal[0] : scal[1];
-  float* p = i < na ? pa + i : pc + (i - na_pad);
-  *p = *p - step * (mi / denom);
+  const int t = *step_ctr + 1;                            // this launch is optimiser step t
+  const float* scal = scal_ring + 4 * (t & 1);
+  const int64_t writer = na < na_pad ? na : ((n & 255) ? n : 0);   // an idle thread of the grid if there is one
+  if (i == writer) adam_scalars(t + 1, lr_a, lr_c, b1, b2, scal_ring + 4 * ((t + 1) & 1));
+  const bool live = i < n && !(i >= na && i < na_pad);
+  if (live) {
+    const float gi = g[i], m0 = m[i], v0 = v[i];
+    float mi = m0 + (gi - m0) * (1.0f - b1);            // exp_avg.lerp_(grad, 1-beta1)
+    float vi = v0 * b2 + (1.0f - b2) * gi * gi;         // mul_(beta2).addcmul_(g, g, 1-beta2)
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / scal[2] + eps;
+    float step = i < na ? scal[0] : scal[1];
+    float* p = i < na ? pa + i : pc + (i - na_pad);
+    *p = *p - step * (mi / denom);
+  }
+  __syncthreads();                                        // the ring writer, if it is in this block
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {       // every block has read the counter: advance it
+      *ticket = 0u;
+      *step_ctr = *step_ctr + 1;
+    }
+  }
 }
 
 // ---- fused gradient sum over ranks + Adam through NVLink peer memory -----------------------------------------
@@ -420,13 +440,17 @@ __device__ __forceinline__ bool spin_until_ge(const int* p, int target, int* tim
 
 __global__ void __launch_bounds__(256) adam_p2p_kernel(P2PArgs pa, float* __restrict__ p_actor, float* __restrict__ p_critic,
                                                        float* __restrict__ m, float* __restrict__ v, int64_t na,
-                                                       int64_t na_pad, int64_t n, const float* __restrict__ scal, float b1,
-                                                       float b2, float eps) {
+                                                       int64_t na_pad, int64_t n, int* step_ctr, float* scal_ring,
+                                                       float lr_a, float lr_c, float b1, float b2, float eps) {
   int* mine = pa.sync[pa.rank];
   if (ld_acquire_sys(mine + PS_TIMEOUT) != 0) return;   // sticky: a previous launch timed out, the replica is frozen
   const int epoch = mine[PS_EPOCH] + 1;   // written only by the last block of the previous launch (stream ordered)
   __shared__ int ok_s;
   if (threadIdx.x == 0) ok_s = 1;
+  const int t_opt = *step_ctr + 1;                        // this launch is optimiser step t_opt
+  const float* scal = scal_ring + 4 * (t_opt & 1);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 32)   // next step's scalars, off the critical path
+    adam_scalars(t_opt + 1, lr_a, lr_c, b1, b2, scal_ring + 4 * ((t_opt + 1) & 1));
   __syncthreads();
   if (blockIdx.x == 0) {
     // "ready": tell every rank that this rank's gradients are complete, then wait for everybody
@@ -462,6 +486,7 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(P2PArgs pa, float* __rest
     const int prev = atomicAdd(mine + PS_COUNT, 1);
     if (prev == (int)gridDim.x - 1) {
       mine[PS_COUNT] = 0;
+      *step_ctr = *step_ctr + 1;           // every block has read it
       for (int q = 0; q < pa.world; ++q) st_release_sys(pa.sync[q] + PS_DONE + pa.rank, epoch);
       for (int q = 0; q < pa.world; ++q) spin_until_ge(mine + PS_DONE + q, epoch, mine + PS_TIMEOUT);
       st_release_sys(mine + PS_EPOCH, epoch);
@@ -602,7 +627,7 @@ extern "C" int bmi_ddpg_create(bmi_ddpg** out, const bmi_ddpg_config* cfg, float
   h->n_grads = h->na_pad + h->lc.count;
   const int64_t np = h->n_grads;
 #define A_(p, n) if (!rc) rc = dalloc(h, &h->p, (size_t)(n))
-  A_(grads, np); A_(adam_m, np); A_(adam_v, np); A_(adam_scal, 4);
+  A_(grads, np); A_(adam_m, np); A_(adam_v, np); A_(adam_scal, 8);
   A_(xc, B * (Dx + Da)); A_(h1, B * H); A_(h2, B * H); A_(h3, B * H);
   A_(ch1, B * H); A_(ch2, B * H); A_(ch3, B * H); A_(q, B);
   A_(ah1, B * H); A_(ah2, B * H); A_(ah3, B * H); A_(az, B * Da); A_(aa, B * Da);
@@ -623,12 +648,22 @@ extern "C" int bmi_ddpg_create(bmi_ddpg** out, const bmi_ddpg_config* cfg, float
 #undef A_
   if (!rc) {
     void* p = nullptr;
-    if (cudaMalloc(&p, sizeof(unsigned) * ((H + 31) / 32)) != cudaSuccess || cudaMemset(p, 0, sizeof(unsigned) * ((H + 31) / 32)) != cudaSuccess) {
+    const size_t nt = (size_t)(H + 31) / 32 + 1;
+    if (cudaMalloc(&p, sizeof(unsigned) * nt) != cudaSuccess || cudaMemset(p, 0, sizeof(unsigned) * nt) != cudaSuccess) {
       set_error("bmi_ddpg_create: cudaMalloc(tickets) failed");
       rc = BMI_ERR_CUDA;
     } else {
       h->owned.push_back(p);
       h->bg_ticket = (unsigned*)p;
+      h->adam_ticket = (unsigned*)p + (nt - 1);
+    }
+  }
+  if (!rc) {   // Adam step sizes of step 1 (slot 1 of the ring); every launch prepares its successor's
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+    adam_scalars(1, cfg->lr_actor, cfg->lr_critic, cfg->adam_beta1, cfg->adam_beta2, sc);
+    if (cudaMemcpy(h->adam_scal + 4, sc, sizeof(sc), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("bmi_ddpg_create: cudaMemcpy(adam scalars) failed");
+      rc = BMI_ERR_CUDA;
     }
   }
   if (!rc) {   // d(-mean Q)/dQ of the actor loss: constant, written once
@@ -740,11 +775,11 @@ extern "C" int bmi_ddpg_backward(bmi_ddpg* h, const float* x, const float* xn, c
       wg.D[p] = Dp[p]; wg.Ac[p] = Ap[p]; wg.gW[p] = gWp[p]; wg.gb[p] = gbp[p];
       wg.ldD[p] = ldD[p]; wg.ldA[p] = ldA[p]; wg.Nj[p] = Nj[p]; wg.Nk[p] = Nk[p];
       wg.tile0[p] = tiles;
-      tiles += ((Nj[p] + WG_TJ - 1) / WG_TJ) * ((Nk[p] + WG_TK - 1) / WG_TK);
+      tiles += Nj[p] <= FOUT ? 1 : ((Nj[p] + WG_TJ - 1) / WG_TJ) * ((Nk[p] + WG_TK - 1) / WG_TK);   // output layers: one CTA
     }
     wg.tile0[WG_P] = tiles;
     wg.loss_part = h->loss_part; wg.losses = losses; wg.n_part = B / FR; wg.B = B; wg.Da = Da; wg.l2 = c.action_l2;
-    ddpg_wgrad_kernel<<<tiles, 256, 0, st>>>(wg);
+    ddpg_wgrad_kernel<<<tiles, WG_T, 0, st>>>(wg);
     BMI_LAUNCHED();
     return BMI_OK;
   }
@@ -791,12 +826,10 @@ extern "C" int bmi_ddpg_adam_step(bmi_ddpg* h, bmi_stream_t stream) {
   BMI_REQUIRE(h, "bmi_ddpg_adam_step: null handle");
   cudaStream_t st = as_stream(stream);
   const bmi_ddpg_config& c = h->cfg;
-  adam_prepare_kernel<<<1, 1, 0, st>>>(h->adam_step, h->adam_scal, c.lr_actor, c.lr_critic, c.adam_beta1, c.adam_beta2);
-  BMI_LAUNCHED();
   const int64_t n = h->n_grads;
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->actor, h->critic, h->grads, h->adam_m, h->adam_v,
-                                                            h->la.count, h->na_pad, n, h->adam_scal, c.adam_beta1,
-                                                            c.adam_beta2, c.adam_eps);
+                                                            h->la.count, h->na_pad, n, h->adam_step, h->adam_ticket,
+                                                            h->adam_scal, c.lr_actor, c.lr_critic, c.adam_beta1, c.adam_beta2, c.adam_eps);
   BMI_LAUNCHED();
   return BMI_OK;
 }
@@ -848,14 +881,12 @@ extern "C" int bmi_ddpg_adam_step_p2p(bmi_ddpg* h, bmi_stream_t stream) {
   BMI_REQUIRE(h->p2p_world >= 1 && h->peer_grads[h->p2p_rank] != nullptr, "bmi_ddpg_adam_step_p2p: peers not attached");
   cudaStream_t st = as_stream(stream);
   const bmi_ddpg_config& c = h->cfg;
-  adam_prepare_kernel<<<1, 1, 0, st>>>(h->adam_step, h->adam_scal, c.lr_actor, c.lr_critic, c.adam_beta1, c.adam_beta2);
-  BMI_LAUNCHED();
   P2PArgs pa;
   for (int q = 0; q < 8; ++q) { pa.grads[q] = h->peer_grads[q]; pa.sync[q] = h->peer_sync[q]; }
   pa.rank = h->p2p_rank;
   pa.world = h->p2p_world;
   adam_p2p_kernel<<<64, 256, 0, st>>>(pa, h->actor, h->critic, h->adam_m, h->adam_v, h->la.count, h->na_pad, h->n_grads,
-                                      h->adam_scal, c.adam_beta1, c.adam_beta2, c.adam_eps);
+                                      h->adam_step, h->adam_scal, c.lr_actor, c.lr_critic, c.adam_beta1, c.adam_beta2, c.adam_eps);
   BMI_LAUNCHED();
   return BMI_OK;
 }

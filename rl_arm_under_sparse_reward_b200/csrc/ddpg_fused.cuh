@@ -12,7 +12,7 @@
 //                      weights with the lane owning a slice of the layer's INPUT, so they need no lane reduction at all, only a
 //                      sum over the 8 warps through shared memory.  Activations and deltas go to global memory for ...
 //   ddpg_wgrad_kernel  ... the weight / bias gradients: 8 products  dW = delta^T . activation  (sum over the batch rows) as
-//                      32 x 64 output tiles (144 CTAs, one wave), classic shared-memory fp32 GEMM with register prefetch; the
+//                      32 x 64 output tiles (152 CTAs of 128 threads, 4 x 4 outputs per thread), shared-memory fp32 GEMM with register prefetch; the
 //                      CTAs of the first tile column also produce the bias gradients, CTA 0 the two scalar losses.
 //
 // The layer routines are deliberately NOT inlined: the kernel runs 33 layer steps back to back without a loop, and inlined it
@@ -62,11 +62,22 @@ __device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// out[r][j] = act(b[j] + sum_k W[j][k] in[r][k]),  W [FH][FH] row-major.  in / out: shared [FR][FH]; gout: global rows or null
+// out[r][j] = act(b[j] + sum_k W[j][k] in[r][k]),  W [FH][FH] row-major.  in / out: shared [FR][FH]; gout: global rows or null.
+// STARTS with the barrier that makes `in` visible -- after the first batch of weight loads has been issued, so that their L2
+// latency overlaps the wait; inside, the loads of batch b + 1 are in flight while batch b is multiplied.
 template <bool RELU>
 __device__ __noinline__ void f_fwd_hidden(const float* __restrict__ W, const float* __restrict__ b, const float* in,
-                                             float* out, float* gout) {
+                                          float* out, float* gout) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const float4* Wp = reinterpret_cast<const float4*>(W + (size_t)(w * 32) * FH) + l;   // row jj: + jj * 64 float4
+  float4 a[2][8], c[2][8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    a[0][u] = __ldg(Wp + u * 64);
+    c[0][u] = __ldg(Wp + u * 64 + 32);
+  }
+  const float bj = __ldg(b + threadIdx.x);
+  __syncthreads();
   float4 i0[FR], i1[FR];
 #pragma unroll
   for (int r = 0; r < FR; ++r) {
@@ -74,21 +85,20 @@ __device__ __noinline__ void f_fwd_hidden(const float* __restrict__ W, const flo
     i1[r] = *reinterpret_cast<const float4*>(in + r * FH + 128 + l * 4);
   }
   float acc[FR][32];
-  const float4* Wp = reinterpret_cast<const float4*>(W + (size_t)(w * 32) * FH) + l;   // row jj: + jj * 64 float4
 #pragma unroll
-  for (int j0 = 0; j0 < 32; j0 += 8) {
-    float4 a[8], c[8];
+  for (int g = 0; g < 4; ++g) {
+    if (g < 3) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      a[u] = __ldg(Wp + (j0 + u) * 64);
-      c[u] = __ldg(Wp + (j0 + u) * 64 + 32);
+      for (int u = 0; u < 8; ++u) {
+        a[(g + 1) & 1][u] = __ldg(Wp + ((g + 1) * 8 + u) * 64);
+        c[(g + 1) & 1][u] = __ldg(Wp + ((g + 1) * 8 + u) * 64 + 32);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int r = 0; r < FR; ++r) acc[r][j0 + u] = dot4(a[u], i0[r]) + dot4(c[u], i1[r]);
+      for (int r = 0; r < FR; ++r) acc[r][g * 8 + u] = dot4(a[g & 1][u], i0[r]) + dot4(c[g & 1][u], i1[r]);
   }
-  const float bj = __ldg(b + threadIdx.x);
 #pragma unroll
   for (int r = 0; r < FR; ++r) {
     float v = butterfly32(acc[r], l) + bj;          // lane l: neuron w * 32 + l == threadIdx.x
@@ -98,10 +108,20 @@ __device__ __noinline__ void f_fwd_hidden(const float* __restrict__ W, const flo
   }
 }
 
-// first layer: out[r][j] = relu(b[j] + sum_{k < K} W[j][k] in[r][k]),  W [FH][K] row-major, K <= 64; in: shared [FR][FIN]
+// first layer: out[r][j] = relu(b[j] + sum_{k < K} W[j][k] in[r][k]),  W [FH][K] row-major, K <= 64; in: shared [FR][FIN].
+// Starts with the barrier that makes `in` visible (after its weight loads have been issued)
 __device__ __noinline__ void f_fwd_first(const float* __restrict__ W, const float* __restrict__ b, const float* in, int K,
-                                            float* out, float* gout) {
+                                         float* out, float* gout) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const float* Wp = W + (size_t)(w * 32) * K;
+  float a[32], c[32];                           // the whole 32 x K slab of this warp: at most 64 loads per lane, all in flight
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    a[u] = l < K ? __ldg(Wp + u * K + l) : 0.f;
+    c[u] = l + 32 < K ? __ldg(Wp + u * K + 32 + l) : 0.f;
+  }
+  const float bj = __ldg(b + threadIdx.x);
+  __syncthreads();
   float i0[FR], i1[FR];
 #pragma unroll
   for (int r = 0; r < FR; ++r) {
@@ -109,21 +129,10 @@ __device__ __noinline__ void f_fwd_first(const float* __restrict__ W, const floa
     i1[r] = l + 32 < K ? in[r * FIN + 32 + l] : 0.f;
   }
   float acc[FR][32];
-  const float* Wp = W + (size_t)(w * 32) * K;
 #pragma unroll
-  for (int j0 = 0; j0 < 32; j0 += 8) {
-    float a[8], c[8];
+  for (int u = 0; u < 32; ++u)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      a[u] = l < K ? __ldg(Wp + (j0 + u) * K + l) : 0.f;
-      c[u] = l + 32 < K ? __ldg(Wp + (j0 + u) * K + 32 + l) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-#pragma unroll
-      for (int r = 0; r < FR; ++r) acc[r][j0 + u] = fmaf(c[u], i1[r], a[u] * i0[r]);
-  }
-  const float bj = __ldg(b + threadIdx.x);
+    for (int r = 0; r < FR; ++r) acc[r][u] = fmaf(c[u], i1[r], a[u] * i0[r]);
 #pragma unroll
   for (int r = 0; r < FR; ++r) {
     const float v = fmaxf(butterfly32(acc[r], l) + bj, 0.f);
@@ -132,20 +141,28 @@ __device__ __noinline__ void f_fwd_first(const float* __restrict__ W, const floa
   }
 }
 
-// output layer: z[r][j] = b[j] + sum_k W[j][k] in[r][k],  j < N <= FOUT (one warp per output); z: shared [FR][FOUT]
+// output layer: z[r][j] = b[j] + sum_k W[j][k] in[r][k],  j < N <= FOUT (one warp per output); z: shared [FR][FOUT].
+// Starts with the barrier that makes `in` visible
 __device__ __noinline__ void f_fwd_out(const float* __restrict__ W, const float* __restrict__ b, const float* in, int N,
-                                          float* z) {
+                                       float* z) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+  float bw = 0.f;
+  if (w < N) {
+    const float4* Wp = reinterpret_cast<const float4*>(W + (size_t)w * FH) + l;
+    a = __ldg(Wp);
+    c = __ldg(Wp + 32);
+    bw = __ldg(b + w);
+  }
+  __syncthreads();
   if (w >= N) return;
-  const float4* Wp = reinterpret_cast<const float4*>(W + (size_t)w * FH) + l;
-  const float4 a = __ldg(Wp), c = __ldg(Wp + 32);
 #pragma unroll
   for (int r = 0; r < FR; ++r) {
     float v = dot4(a, *reinterpret_cast<const float4*>(in + r * FH + l * 4)) +
               dot4(c, *reinterpret_cast<const float4*>(in + r * FH + 128 + l * 4));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (l == 0) z[r * FOUT + w] = v + __ldg(b + w);
+    if (l == 0) z[r * FOUT + w] = v + bw;
   }
 }
 
@@ -169,34 +186,44 @@ __device__ __noinline__ void f_bwd_out(const float* __restrict__ W, const float*
   }
 }
 
-// delta below a hidden layer: dx[r][k] = [h[r][k] > 0] sum_j dy[r][j] W[j][k].  Contains a __syncthreads (partial sums of
-// the 8 warps in part [FW][FR][FH]); dy / h / dx: shared [FR][FH], dx must not alias dy
+// delta below a hidden layer: dx[r][k] = [h[r][k] > 0] sum_j dy[r][j] W[j][k].  Starts with the barrier that makes dy visible
+// (after the first weight loads) and contains a second one (partial sums of the 8 warps in part [FW][FR][FH]);
+// dy / h / dx: shared [FR][FH], dx must not alias dy
 __device__ __noinline__ void f_bwd_hidden(const float* __restrict__ W, const float* dy, const float* h, float* dx,
-                                             float* gdx, float* part) {
+                                          float* gdx, float* part) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const float4* Wp = reinterpret_cast<const float4*>(W + (size_t)(w * 32) * FH) + l;
+  float4 a[2][8], c[2][8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    a[0][u] = __ldg(Wp + u * 64);
+    c[0][u] = __ldg(Wp + u * 64 + 32);
+  }
+  __syncthreads();                               // dy (and h) visible; part free again
   float4 a0[FR], a1[FR];
 #pragma unroll
   for (int r = 0; r < FR; ++r) a0[r] = a1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4* Wp = reinterpret_cast<const float4*>(W + (size_t)(w * 32) * FH) + l;
 #pragma unroll
-  for (int j0 = 0; j0 < 32; j0 += 8) {
-    float4 a[8], c[8];
+  for (int g = 0; g < 4; ++g) {
+    if (g < 3) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      a[u] = __ldg(Wp + (j0 + u) * 64);
-      c[u] = __ldg(Wp + (j0 + u) * 64 + 32);
+      for (int u = 0; u < 8; ++u) {
+        a[(g + 1) & 1][u] = __ldg(Wp + ((g + 1) * 8 + u) * 64);
+        c[(g + 1) & 1][u] = __ldg(Wp + ((g + 1) * 8 + u) * 64 + 32);
+      }
     }
 #pragma unroll
     for (int r = 0; r < FR; ++r) {
-      const float4 d0 = *reinterpret_cast<const float4*>(dy + r * FH + w * 32 + j0);
-      const float4 d1 = *reinterpret_cast<const float4*>(dy + r * FH + w * 32 + j0 + 4);
+      const float4 d0 = *reinterpret_cast<const float4*>(dy + r * FH + w * 32 + g * 8);
+      const float4 d1 = *reinterpret_cast<const float4*>(dy + r * FH + w * 32 + g * 8 + 4);
       const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        a0[r].x = fmaf(d[u], a[u].x, a0[r].x); a0[r].y = fmaf(d[u], a[u].y, a0[r].y);
-        a0[r].z = fmaf(d[u], a[u].z, a0[r].z); a0[r].w = fmaf(d[u], a[u].w, a0[r].w);
-        a1[r].x = fmaf(d[u], c[u].x, a1[r].x); a1[r].y = fmaf(d[u], c[u].y, a1[r].y);
-        a1[r].z = fmaf(d[u], c[u].z, a1[r].z); a1[r].w = fmaf(d[u], c[u].w, a1[r].w);
+        const float4 wa = a[g & 1][u], wc = c[g & 1][u];
+        a0[r].x = fmaf(d[u], wa.x, a0[r].x); a0[r].y = fmaf(d[u], wa.y, a0[r].y);
+        a0[r].z = fmaf(d[u], wa.z, a0[r].z); a0[r].w = fmaf(d[u], wa.w, a0[r].w);
+        a1[r].x = fmaf(d[u], wc.x, a1[r].x); a1[r].y = fmaf(d[u], wc.y, a1[r].y);
+        a1[r].z = fmaf(d[u], wc.z, a1[r].z); a1[r].w = fmaf(d[u], wc.w, a1[r].w);
       }
     }
   }
@@ -264,6 +291,7 @@ __global__ void __launch_bounds__(FT, 1) ddpg_rows_kernel(const FusedArgs A) {
   const size_t g0 = (size_t)row0 * FH;      // this CTA's rows in the [B][FH] global arrays
 
   // ---- inputs -------------------------------------------------------------------------------------------------------------
+  // (f_fwd_first / f_fwd_hidden / f_fwd_out / f_bwd_hidden START with the barrier that publishes what was written before them)
   for (int i = t; i < FR * FIN; i += FT) {
     const int r = i / FIN, k = i - r * FIN;
     const size_t row = row0 + r;
@@ -277,15 +305,11 @@ __global__ void __launch_bounds__(FT, 1) ddpg_rows_kernel(const FusedArgs A) {
     s_in[0][i] = vn; s_in[1][i] = vc; s_in[2][i] = va;
     if (k < Dc) A.xc[row * Dc + k] = vc;
   }
-  __syncthreads();
 
   // ---- target: y = clamp(r + gamma Q'(x', pi'(x')), -clip, 0)  (ddpg_agent.py:252-260) ---------------------------------------
   f_fwd_first(Pat + A.wa[0], Pat + A.ba[0], s_in[0], Dx, sA, nullptr);
-  __syncthreads();
   f_fwd_hidden<true>(Pat + A.wa[1], Pat + A.ba[1], sA, sB, nullptr);
-  __syncthreads();
   f_fwd_hidden<true>(Pat + A.wa[2], Pat + A.ba[2], sB, sA, nullptr);
-  __syncthreads();
   f_fwd_out(Pat + A.wa[3], Pat + A.ba[3], sA, Da, s_z);
   __syncthreads();
   if (t < FR * Da) {
@@ -293,23 +317,15 @@ __global__ void __launch_bounds__(FT, 1) ddpg_rows_kernel(const FusedArgs A) {
     const float a = A.amax * tanhf(s_z[r * FOUT + c]);
     s_in[0][r * FIN + Dx + c] = __fdiv_rn(a, A.amax);
   }
-  __syncthreads();
   f_fwd_first(Pct + A.wc[0], Pct + A.bc[0], s_in[0], Dc, sA, nullptr);
-  __syncthreads();
   f_fwd_hidden<true>(Pct + A.wc[1], Pct + A.bc[1], sA, sB, nullptr);
-  __syncthreads();
   f_fwd_hidden<true>(Pct + A.wc[2], Pct + A.bc[2], sB, sA, nullptr);
-  __syncthreads();
   f_fwd_out(Pct + A.wc[3], Pct + A.bc[3], sA, 1, s_qn);
-  __syncthreads();
 
   // ---- critic(x, a): forward, loss, delta chain (ddpg_agent.py:262-263,274-275) ---------------------------------------------
   f_fwd_first(Pc + A.wc[0], Pc + A.bc[0], s_in[1], Dc, ch1, A.ch1 + g0);
-  __syncthreads();
   f_fwd_hidden<true>(Pc + A.wc[1], Pc + A.bc[1], ch1, ch2, A.ch2 + g0);
-  __syncthreads();
   f_fwd_hidden<true>(Pc + A.wc[2], Pc + A.bc[2], ch2, ch3, A.ch3 + g0);
-  __syncthreads();
   f_fwd_out(Pc + A.wc[3], Pc + A.bc[3], ch3, 1, s_q);
   __syncthreads();
   float l_c = 0.f, l_q = 0.f, l_t = 0.f;     // thread 0: loss partial sums of this CTA
@@ -326,19 +342,13 @@ __global__ void __launch_bounds__(FT, 1) ddpg_rows_kernel(const FusedArgs A) {
   }
   __syncthreads();
   f_bwd_out(Pc + A.wc[3], s_dz, 1, ch3, sD0, A.cd3 + g0);
-  __syncthreads();
   f_bwd_hidden(Pc + A.wc[2], sD0, ch2, sD1, A.cd2 + g0, s_part);
-  __syncthreads();
   f_bwd_hidden(Pc + A.wc[1], sD1, ch1, sD0, A.cd1 + g0, s_part);
-  __syncthreads();
 
   // ---- actor(x) and critic(x, pi(x)) forward (ddpg_agent.py:265-267) -------------------------------------------------------
   f_fwd_first(Pa + A.wa[0], Pa + A.ba[0], s_in[2], Dx, ah1, A.ah1 + g0);
-  __syncthreads();
   f_fwd_hidden<true>(Pa + A.wa[1], Pa + A.ba[1], ah1, ah2, A.ah2 + g0);
-  __syncthreads();
   f_fwd_hidden<true>(Pa + A.wa[2], Pa + A.ba[2], ah2, ah3, A.ah3 + g0);
-  __syncthreads();
   f_fwd_out(Pa + A.wa[3], Pa + A.ba[3], ah3, Da, s_z);
   __syncthreads();
   if (t < FR * Da) {
@@ -347,22 +357,16 @@ __global__ void __launch_bounds__(FT, 1) ddpg_rows_kernel(const FusedArgs A) {
     s_th[r * FOUT + c] = a / A.amax;
     s_in[2][r * FIN + Dx + c] = __fdiv_rn(a, A.amax);
   }
-  __syncthreads();
   f_fwd_first(Pc + A.wc[0], Pc + A.bc[0], s_in[2], Dc, qh1, nullptr);
-  __syncthreads();
   f_fwd_hidden<true>(Pc + A.wc[1], Pc + A.bc[1], qh1, qh2, nullptr);
-  __syncthreads();
   f_fwd_hidden<true>(Pc + A.wc[2], Pc + A.bc[2], qh2, qh3, nullptr);
-  __syncthreads();
   f_fwd_out(Pc + A.wc[3], Pc + A.bc[3], qh3, 1, s_qa);
-  if (t < FR * FOUT) s_dz[t] = -1.0f / (float)A.B;          // d(-mean Q)/dQ
+  if (t < FR * FOUT) s_dz[t] = -1.0f / (float)A.B;          // d(-mean Q)/dQ   (s_dz: last read two barriers ago)
   __syncthreads();
 
   // ---- dQ/da through the critic, then the actor's delta chain (ddpg_agent.py:266-270) -------------------------------------
   f_bwd_out(Pc + A.wc[3], s_dz, 1, qh3, sD0, nullptr);
-  __syncthreads();
   f_bwd_hidden(Pc + A.wc[2], sD0, qh2, sD1, nullptr, s_part);
-  __syncthreads();
   f_bwd_hidden(Pc + A.wc[1], sD1, qh1, sD0, nullptr, s_part);
   __syncthreads();
   f_bwd_first_cols(Pc + A.wc[0], Dc, Dx, Da, sD0, s_da, s_red);
@@ -387,9 +391,7 @@ __global__ void __launch_bounds__(FT, 1) ddpg_rows_kernel(const FusedArgs A) {
     lp[0] = l_q; lp[1] = l_t; lp[2] = l_c; lp[3] = 0.f;
   }
   f_bwd_out(Pa + A.wa[3], s_dz, Da, ah3, sD0, A.fd3 + g0);
-  __syncthreads();
   f_bwd_hidden(Pa + A.wa[2], sD0, ah2, sD1, A.fd2 + g0, s_part);
-  __syncthreads();
   f_bwd_hidden(Pa + A.wa[1], sD1, ah1, sD0, A.fd1 + g0, s_part);
 }
 
@@ -409,7 +411,8 @@ struct WgradArgs {
   float l2;
 };
 
-__global__ void __launch_bounds__(256) ddpg_wgrad_kernel(const WgradArgs G) {
+constexpr int WG_T = 128;       // threads: 4 (j) x 4 (k) outputs each
+__global__ void __launch_bounds__(WG_T) ddpg_wgrad_kernel(const WgradArgs G) {
   __shared__ __align__(16) float sD[WG_RC][WG_TJ];
   __shared__ __align__(16) float sA[WG_RC][WG_TK];
   const int t = threadIdx.x;
@@ -422,56 +425,7 @@ __global__ void __launch_bounds__(256) ddpg_wgrad_kernel(const WgradArgs G) {
   const int j0 = (tile / tk_n) * WG_TJ, k0 = (tile % tk_n) * WG_TK;
   const float* __restrict__ D = G.D[p];
   const float* __restrict__ Am = G.Ac[p];
-  // staging roles: D chunk 32 x 32 = 4 per thread (row t / 32 + 8 i, col t % 32); A chunk 32 x 64 = 8 per thread
-  const int dc = t & 31, dr = t >> 5, ac = t & 63, ar = t >> 6;
-  const bool d_ok = j0 + dc < Nj, a_ok = k0 + ac < Nk;
-  float pd[4], pa[8];
-  auto fetch = [&](int r0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) pd[i] = d_ok ? D[(size_t)(r0 + dr + 8 * i) * ldD + j0 + dc] : 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) pa[i] = a_ok ? Am[(size_t)(r0 + ar + 4 * i) * ldA + k0 + ac] : 0.f;
-  };
-  // compute roles: thread owns outputs j = jp * 2 + {0, 1}, k = kq * 4 + {0..3}
-  const int kq = t & 15, jp = t >> 4;
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  float bsum = 0.f;                                         // thread t < 32: column sum of D (bias gradient)
-  fetch(0);
-  for (int r0 = 0; r0 < G.B; r0 += WG_RC) {
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sD[dr + 8 * i][dc] = pd[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sA[ar + 4 * i][ac] = pa[i];
-    __syncthreads();
-    if (r0 + WG_RC < G.B) fetch(r0 + WG_RC);
-#pragma unroll
-    for (int r = 0; r < WG_RC; ++r) {
-      const float2 d = *reinterpret_cast<const float2*>(&sD[r][jp * 2]);
-      const float4 a = *reinterpret_cast<const float4*>(&sA[r][kq * 4]);
-      acc[0][0] = fmaf(d.x, a.x, acc[0][0]); acc[0][1] = fmaf(d.x, a.y, acc[0][1]);
-      acc[0][2] = fmaf(d.x, a.z, acc[0][2]); acc[0][3] = fmaf(d.x, a.w, acc[0][3]);
-      acc[1][0] = fmaf(d.y, a.x, acc[1][0]); acc[1][1] = fmaf(d.y, a.y, acc[1][1]);
-      acc[1][2] = fmaf(d.y, a.z, acc[1][2]); acc[1][3] = fmaf(d.y, a.w, acc[1][3]);
-    }
-    if (k0 == 0 && t < WG_TJ) {
-#pragma unroll
-      for (int r = 0; r < WG_RC; ++r) bsum += sD[r][t];
-    }
-  }
-  float* __restrict__ gW = G.gW[p];
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    const int j = j0 + jp * 2 + a;
-    if (j >= Nj) continue;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int k = k0 + kq * 4 + b;
-      if (k < Nk) gW[(size_t)j * Nk + k] = acc[a][b];
-    }
-  }
-  if (k0 == 0 && t < WG_TJ && j0 + t < Nj) G.gb[p][j0 + t] = bsum;
-  if (blockIdx.x == 0 && t == 0) {
+  if (blockIdx.x == gridDim.x - 1 && t == WG_T - 1) {     // the two scalar losses (an idle thread of the last tile's epilogue)
     float sq = 0.f, st = 0.f, sc = 0.f;
     for (int i = 0; i < G.n_part; ++i) {
       sq += G.loss_part[i * 4 + 0];
@@ -481,6 +435,104 @@ __global__ void __launch_bounds__(256) ddpg_wgrad_kernel(const WgradArgs G) {
     G.losses[0] = -sq / (float)G.B + G.l2 * st / (float)(G.B * G.Da);
     G.losses[1] = sc / (float)G.B;
   }
+  if (Nj <= FOUT) {
+    // output layers (1 or act_dim rows): ONE CTA for the whole product, so that the grid stays below one CTA per SM
+    // (152 tiles on 148 SMs doubled the kernel's duration: two CTAs shared an SM).  Thread t owns columns t and t + 128.
+    float acc[FOUT][2], bs[FOUT];
+#pragma unroll
+    for (int j = 0; j < FOUT; ++j) acc[j][0] = acc[j][1] = bs[j] = 0.f;
+    const bool k0v = t < Nk, k1v = t + WG_T < Nk;
+    float* sDj = &sA[0][0];                                // [rows of a 256-row block][FOUT], 8 KB of the staging buffer
+    for (int rb = 0; rb < G.B; rb += 256) {
+      const int nr = min(256, G.B - rb);
+      __syncthreads();
+      for (int i = t; i < nr * FOUT; i += WG_T) {
+        const int r = i / FOUT, j = i - r * FOUT;
+        sDj[i] = j < Nj ? D[(size_t)(rb + r) * ldD + j] : 0.f;
+      }
+      __syncthreads();
+      for (int r0 = 0; r0 < nr; r0 += 8) {                 // nr is a multiple of 32 (checked on the host)
+        float a0[8], a1[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          a0[u] = k0v ? Am[(size_t)(rb + r0 + u) * ldA + t] : 0.f;
+          a1[u] = k1v ? Am[(size_t)(rb + r0 + u) * ldA + t + WG_T] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int j = 0; j < FOUT; ++j) {
+            const float d = sDj[(r0 + u) * FOUT + j];
+            acc[j][0] = fmaf(d, a0[u], acc[j][0]);
+            acc[j][1] = fmaf(d, a1[u], acc[j][1]);
+            bs[j] += d;
+          }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < FOUT; ++j) {
+      if (j >= Nj) break;
+      if (k0v) G.gW[p][(size_t)j * Nk + t] = acc[j][0];
+      if (k1v) G.gW[p][(size_t)j * Nk + t + WG_T] = acc[j][1];
+      if (t == 0) G.gb[p][j] = bs[j];
+    }
+    return;
+  }
+  // staging roles: D chunk 32 x 32 = 8 per thread (row t / 32 + 4 i, col t % 32); A chunk 32 x 64 = 16 per thread
+  const int dc = t & 31, dr = t >> 5, ac = t & 63, ar = t >> 6;
+  const bool d_ok = j0 + dc < Nj, a_ok = k0 + ac < Nk;
+  float pd[8], pa[16];
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pd[i] = d_ok ? D[(size_t)(r0 + dr + 4 * i) * ldD + j0 + dc] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pa[i] = a_ok ? Am[(size_t)(r0 + ar + 2 * i) * ldA + k0 + ac] : 0.f;
+  };
+  // compute roles: thread owns outputs j = jq * 4 + {0..3}, k = kq * 4 + {0..3}: two 16-byte shared loads per 16 FFMA
+  const int kq = t & 15, jq = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float bsum = 0.f;                                         // thread t < 32: column sum of D (bias gradient)
+  fetch(0);
+  for (int r0 = 0; r0 < G.B; r0 += WG_RC) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sD[dr + 4 * i][dc] = pd[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sA[ar + 2 * i][ac] = pa[i];
+    __syncthreads();
+    if (r0 + WG_RC < G.B) fetch(r0 + WG_RC);
+#pragma unroll
+    for (int r = 0; r < WG_RC; ++r) {
+      const float4 d = *reinterpret_cast<const float4*>(&sD[r][jq * 4]);
+      const float4 a = *reinterpret_cast<const float4*>(&sA[r][kq * 4]);
+      const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(dv[i], a.x, acc[i][0]); acc[i][1] = fmaf(dv[i], a.y, acc[i][1]);
+        acc[i][2] = fmaf(dv[i], a.z, acc[i][2]); acc[i][3] = fmaf(dv[i], a.w, acc[i][3]);
+      }
+    }
+    if (k0 == 0 && t < WG_TJ) {
+#pragma unroll
+      for (int r = 0; r < WG_RC; ++r) bsum += sD[r][t];
+    }
+  }
+  float* __restrict__ gW = G.gW[p];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int j = j0 + jq * 4 + a;
+    if (j >= Nj) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int k = k0 + kq * 4 + b;
+      if (k < Nk) gW[(size_t)j * Nk + k] = acc[a][b];
+    }
+  }
+  if (k0 == 0 && t < WG_TJ && j0 + t < Nj) G.gb[p][j0 + t] = bsum;
 }
 
 }  // namespace bmi
