@@ -205,7 +205,10 @@ int bmi_ddpg_destroy(bmi_ddpg* h);
 int bmi_ddpg_act(bmi_ddpg* h, const float* x_dev, int64_t n, int32_t use_target,
                  float* actions_dev, bmi_stream_t stream);
 
-/* ddpg_agent._update_network up to and including both backward passes
+/* With hidden == 256, batch % 32 == 0, obs + goal + act <= 64 and act <= 8 (the reference's shapes) this is two hand-written
+ * kernels (csrc/ddpg_fused.cuh); otherwise, or with BMI_DDPG_CUBLAS=1 in the environment at bmi_ddpg_create time, a chain
+ * of cuBLASLt GEMMs + small kernels.  Same results up to fp32 summation order.
+ * ddpg_agent._update_network up to and including both backward passes
  * (ddpg_agent.py:250-270,274-275): fills the flat gradient buffers (actor then critic,
  * contiguous: one allreduce covers both — utils.py:43-48 sums, it does not average) and
  * writes losses_dev[0] = actor_loss, losses_dev[1] = critic_loss. */
@@ -223,8 +226,9 @@ int bmi_ddpg_adam_step(bmi_ddpg* h, bmi_stream_t stream);
  * adds them in rank order and updates the local replica; two flag barriers in peer memory order it against the
  * neighbours' backward passes.  Set-up: every rank calls bmi_ddpg_p2p_export (128 bytes: two cudaIpcMemHandle_t),
  * the caller all-gathers them, then bmi_ddpg_p2p_attach(rank, world, world x 128 bytes).  world <= 8.
- * bmi_ddpg_p2p_status reports whether a flag wait ever timed out (about one second; the kernel then proceeds
- * instead of hanging the GPU, and the results must be discarded). */
+ * bmi_ddpg_p2p_status reports whether a flag wait ever timed out (about 30 s of SM clocks).  A time-out is FATAL and
+ * sticky: that launch and every later one return without touching the parameters, so the replicas cannot diverge
+ * silently; the caller must stop (ddpg_agent.learn raises). */
 int bmi_ddpg_p2p_export(bmi_ddpg* h, void* handles128_host);
 int bmi_ddpg_p2p_attach(bmi_ddpg* h, int32_t rank, int32_t world, const void* all_handles_host);
 int bmi_ddpg_adam_step_p2p(bmi_ddpg* h, bmi_stream_t stream);
