@@ -18,7 +18,8 @@ for task in ("push", "pick"):
     env.reset(); env.step(torch.zeros(64, 4, device="cuda"))   # env_reset_kernel, env_step_kernel
     ag.buffer.store_episode([ag.ep['obs'], ag.ep['ag'], ag.ep['g'], ag.ep['actions']])
     ag._update_normalizer()                         # her_draw, her gather, norm_update
-    ag.update_many(2)                               # her_inputs_kernel, learner kernels, adam
+    ag.update_many(2)                               # her_inputs_lane_kernel (4-sample chunks), ddpg_rows / ddpg_wgrad, adam
+    ag._sample_batches(80)                          # her_inputs_lane_kernel, 16-sample chunks (20 480 samples)
     ag._soft_update_target_network()
     torch.cuda.synchronize()
     print(task, "ok", ag.losses())
