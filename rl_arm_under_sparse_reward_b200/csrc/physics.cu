@@ -1095,12 +1095,14 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
     if (!fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, false, TRACK);                               \
     int j = fwd_ ? 0 : NL - 1;                                                            \
     const int jstep_ = fwd_ ? 1 : -1;                                                     \
+    /* clamp(lam + x, -m, m) - lam == clamp(x, -m - lam, m - lam): a joint lane's motor impulse only changes at its own */ \
+    /* row, so the two bounds are per-sweep constants and a row is FFMA + 2 FMNMX instead of FFMA + 2 FADD + 2 FMNMX */   \
+    const float mlo_ = -max_imp - lam0, mhi_ = max_imp - lam0;                            \
     _Pragma("unroll (kMotorUnroll)")                                                      \
     for (int jj = 0; jj < NL; ++jj, j += jstep_) {                                        \
-      const float cand = fminf(fmaxf(lam0 + fmaf(-v0, inv0, rhs0), -max_imp), max_imp);   \
-      const float d = cand - lam0;                                                        \
+      const float d = fminf(fmaxf(fmaf(-v0, inv0, rhs0), mlo_), mhi_);                    \
       const float dj = __shfl_sync(FULL, d, j);                                           \
-      if (lane == j) { lam0 = cand; if (TRACK) dl0 = d; }                                 \
+      if (lane == j) { lam0 += d; if (TRACK) dl0 = d; }                                   \
       BMI_JOINT_EVENT(ARM, 4u * (unsigned)j, dj);                                         \
     }                                                                                     \
     if (fwd_ && limit_mask) BMI_LIMIT_ROWS(ARM, true, TRACK);                                 \
@@ -1126,10 +1128,9 @@ _Pragma("unroll 1") \
       const int c = __ffs(m) - 1; \
       const unsigned a = ca + (unsigned)c * (3u * SS * 4u); \
       const float c0 = lds_f(a), c1 = lds_f(a + 4u), c2 = lds_f(a + 8u); \
-      const float cand = fmaxf(fmaf(kf, fmaf(-v0, inv0, rhs0), lam0), 0.f); \
-      const float d = cand - lam0; \
+      const float d = fmaxf(kf * fmaf(-v0, inv0, rhs0), -lam0);   /* max(lam + k x, 0) - lam */ \
       const float dc = __shfl_sync(FULL, d, LANE_CT + c); \
-      if (myc == c) { lam0 = cand; if (TRACKC) dl0 = d; } \
+      if (myc == c) { lam0 += d; if (TRACKC) dl0 = d; } \
       v0 = fmaf(c0, dc, v0); v1 = fmaf(c1, dc, v1); v2 = fmaf(c2, dc, v2); \
     } \
 _Pragma("unroll 1") \
