@@ -30,7 +30,7 @@ def _seeded(seed):
 class Trainer:
     """thin test harness around the C-ABI learner"""
 
-    def __init__(self, L, batch=256, max_rows=512):
+    def __init__(self, L, batch=256, max_rows=512, dims=(27, 3, 4), amax=0.5, gamma=0.98, l2=1.0):
         from rl_arm_under_sparse_reward_b200 import _lib
         self._lib = _lib
         dev = torch.device("cuda")
@@ -38,8 +38,8 @@ class Trainer:
         self.pc = do.flat_params(L.critic).to(dev).contiguous()
         self.ta = do.flat_params(L.actor_t).to(dev).contiguous()
         self.tc = do.flat_params(L.critic_t).to(dev).contiguous()
-        self.cfg = _lib.DdpgConfig(27, 3, 4, 256, batch, max_rows, 0.5, 0.98, 1.0, 1e-3, 1e-3, 0.95, 0.9, 0.999, 1e-8,
-                                   float(1.0 / (1.0 - 0.98)), float(1.0 - 0.95), 0.0)
+        self.cfg = _lib.DdpgConfig(dims[0], dims[1], dims[2], 256, batch, max_rows, amax, gamma, l2, 1e-3, 1e-3, 0.95, 0.9, 0.999,
+                                   1e-8, float(1.0 / (1.0 - gamma)), float(1.0 - 0.95), 0.0)
         self.h = ctypes.c_void_p()
         _lib.call("bmi_ddpg_create", ctypes.byref(self.h), ctypes.byref(self.cfg), _lib.ptr(self.pa), _lib.ptr(self.pc),
                   _lib.ptr(self.ta), _lib.ptr(self.tc))
@@ -134,6 +134,35 @@ def test_fused_update_matches_cublaslt_chain(monkeypatch):
         assert np.abs(mine - ref).max() <= 1e-4 * scale + 1e-9, np.abs(mine - ref).max() / scale
         assert np.linalg.norm(mine - ref) <= 2e-5 * np.linalg.norm(ref)
     assert np.all(out["fused"][1][2] == 0)
+
+
+@pytest.mark.parametrize("dims,batch,amax,gamma,l2", [((40, 5, 7), 96, 1.0, 0.9, 0.5), ((10, 2, 1), 32, 0.25, 0.95, 0.0),
+                                                     ((27, 3, 4), 1024, 0.5, 0.98, 1.0)])
+def test_fused_update_other_shapes_vs_torch_oracle(dims, batch, amax, gamma, l2):
+    """The two-launch update is not specialised to 27 + 3 + 4 / batch 256: other input widths (up to 64 with the action), action
+    counts (up to 8) and batch sizes (multiples of 32) against the torch oracle, same tolerances as the reference shape."""
+    torch.set_num_threads(1)
+    torch.manual_seed(3)
+    L = do.Learner(n_obs=dims[0], n_goal=dims[1], n_act=dims[2], max_action=amax, gamma=gamma, action_l2=l2)
+    T = Trainer(L, batch=batch, dims=dims, amax=amax, gamma=gamma, l2=l2)
+    rng = np.random.RandomState(5)
+    Dx = dims[0] + dims[1]
+    x = np.clip(rng.standard_normal((batch, Dx)), -5, 5).astype(np.float32)
+    xn = np.clip(x + 0.1 * rng.standard_normal((batch, Dx)), -5, 5).astype(np.float32)
+    a = rng.uniform(-amax, amax, (batch, dims[2])).astype(np.float32)
+    r = -(rng.uniform(size=(batch, 1)) > 0.2).astype(np.float32)
+    la, lc, ga, gc = L.losses_and_grads(torch.tensor(x), torch.tensor(xn), torch.tensor(a), torch.tensor(r))
+    n0 = T._lib.launch_count()
+    T.backward(x, xn, a, r)
+    assert T._lib.launch_count() - n0 == 2                   # the fused path was taken
+    assert np.allclose(T.losses.cpu().numpy(), [la, lc], rtol=1e-4, atol=1e-6), (T.losses.cpu().numpy(), la, lc)
+    mya, myc, pad = T.grads()
+    assert np.all(pad == 0)
+    for mine, ref in ((mya, ga.numpy()), (myc, gc.numpy())):
+        scale = np.abs(ref).max()
+        assert np.abs(mine - ref).max() <= 2e-4 * scale + 1e-8, np.abs(mine - ref).max() / scale
+        assert np.linalg.norm(mine - ref) <= 1e-4 * np.linalg.norm(ref)
+    T.close()
 
 
 def test_actor_forward_matches_torch():
