@@ -291,6 +291,17 @@ def run_replay_stress(args):
         t = float(t.item())
         rows.append({"batch": B, "us": t * 1e6, "transitions_per_s": world * B / t, "GB_s_per_gpu": B * 516 / t / 1e9,
                      "frac_of_hbm_peak": B * 516 / t / 1e9 / peak})
+    # the protocol's own floor: the same flush + event pair around a one-element fill kernel
+    tiny = torch.zeros(1, device=dev)
+    fl = []
+    for _ in range(max(args.steps, 10)):
+        flush.fill_(0.0)
+        flush_sink.copy_(flush.sum())
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); tiny.fill_(1.0); e.record()
+        torch.cuda.synchronize()
+        fl.append(s.elapsed_time(e))
+    floor_us = float(np.median(fl)) * 1e3
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=2)
@@ -305,7 +316,8 @@ def run_replay_stress(args):
                            "parallelism": "dp%d (one buffer per rank, no data-path collective)" % world},
                 "roofline": {"bound": "hbm", "achieved": top["GB_s_per_gpu"], "peak": peak, "unit": "GB/s", "frac": top["frac_of_hbm_peak"],
                              "traffic": None, "kernel": "her_inputs_lane_kernel", "algorithmic_bytes_per_launch": 516 * top["batch"],
-                             "peak_source": peak_src, "sweep": rows},
+                             "peak_source": peak_src, "sweep": rows, "launch_floor_us": floor_us,
+                             "launch_floor_note": "same flush + CUDA-event pair around a one-element fill kernel: what a launch costs in this protocol before any sample is gathered"},
                 "cpu_baseline": None,
                 "e2e": None, "gpu_launches": int(_lib.launch_count() - n0), "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
