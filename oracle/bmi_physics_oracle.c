@@ -28,7 +28,7 @@
 #include <string.h>
 
 #include "../include/bmi_model.h"
-#include "convex_epa.h"
+#include "../tools/geom/convex_epa.h"
 
 #define NL 9
 #define NU 15 /* generalized velocities: 9 joints + block linear 3 + block angular 3 */

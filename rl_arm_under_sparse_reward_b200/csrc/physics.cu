@@ -593,7 +593,7 @@ __device__ __noinline__ void push_contacts(Smem& s, const EnvParams& ep, unsigne
   __syncwarp();
 }
 
-// ---- self-collision of the arm: baked pair tables (tools/bake_selfcol.py; oracle: find_self_contacts / sc_lookup) ------
+// ---- self-collision of the arm: baked pair tables (tools/bake_selfcol.py + tools/geom; oracle: find_self_contacts / sc_lookup) -
 // Every link pair that can touch is two joints apart, so the whole narrow phase (signed distance of the two hulls,
 // normal, witness point) is a function of two joint angles, sampled off line with the oracle's GJK + EPA on a 5 mrad
 // grid.  Here: lane = (pair p = lane / 8, node c = (lane / 2) % 4 of the surrounding cell, half = lane % 2 of the

@@ -2,7 +2,7 @@
 (K = 0) and the compressed (K = 2) solver schedule on either side.  Prints error quantiles of the 27-float observation."""
 import os, sys, tempfile
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.physics_oracle import OracleEnv, MODEL
 from rl_arm_under_sparse_reward_b200.bmirobot_env.vec_env import BmiVecEnv
 

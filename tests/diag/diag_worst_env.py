@@ -1,8 +1,8 @@
 """Which observation components carry the worst kernel-vs-oracle one-step errors (tests/test_gpu_physics.py scenario)?
-    python tools/diag_worst_env.py [push|pick]"""
+    python tests/diag/diag_worst_env.py [push|pick]"""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from rl_arm_under_sparse_reward_b200.bmirobot_env.vec_env import BmiVecEnv
 from oracle.physics_oracle import OracleEnv
 

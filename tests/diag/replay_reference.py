@@ -3,12 +3,12 @@ bmirobot_1000_{push,pick}_demo.npz) through the C oracle: the recorded ACTIONS a
 is compared with the recording.  The block's initial yaw is not recorded by the reference, so each
 episode is replayed for 8 yaws and the best final block position counts.  CPU only.
 
-    python tools/replay_reference.py [--mode faithful|kernel] [--procs N]     -> markdown table on stdout
+    python tests/diag/replay_reference.py [--mode faithful|kernel] [--procs N]     -> markdown table on stdout
 """
 import argparse, os, sys
 from multiprocessing import Pool
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle.physics_oracle import OracleEnv
 

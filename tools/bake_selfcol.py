@@ -4,11 +4,12 @@ Every pair of right-arm links that can touch under the reference's self-collisio
 pairs except child/parent) is separated by exactly TWO joints -- the grandparent pairs of the chain and the two
 fingers -- so its narrow phase (signed distance, normal, witness point of the two convex hulls) is a function of two
 joint angles.  The kernel looks that function up instead of running GJK / EPA on 150..750-vertex hulls every sub-step;
-this tool samples it with the oracle's exact GJK / EPA (oracle/convex_epa.h through bmo_pair_query) on a regular grid
-over the two joints' limit box.  Format: include/bmi_model.h (SC_*).
+this tool samples it on a regular grid over the two joints' limit box with tools/geom/pair_table.c (forward kinematics
+of the baked joint tree + exact GJK / EPA, tools/geom/convex_epa.h).  Format: include/bmi_model.h (SC_*).
 
-Needs only files inside the repo (assets/bmirobot_model.bin, assets/bmirobot_hulls.bin, the built oracle library), so it
-runs from __graft_entry__.build(); the output (tens of MB) is git-ignored and travels to the GPU box with the snapshot.
+Product build tooling: needs only assets/bmirobot_model.bin, assets/bmirobot_hulls.bin and gcc -- nothing under
+oracle/ -- so it runs from __graft_entry__.build(); the output (tens of MB) is git-ignored and travels to the GPU box
+with the snapshot.  (tests/test_selfcol_tables.py checks the baked nodes against the test oracle's own narrow phase.)
 
     python tools/bake_selfcol.py [--h 0.005] [--procs N]
 
@@ -21,6 +22,7 @@ These are the only pairs that ever produced a row in 2000 env-steps of random ex
 import argparse
 import ctypes
 import os
+import subprocess
 import sys
 from multiprocessing import Pool
 
@@ -28,7 +30,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-OUT = os.path.join(ROOT, "rl_arm_under_sparse_reward_b200", "assets", "bmirobot_selfcol.bin")
+ASSETS = os.path.join(ROOT, "rl_arm_under_sparse_reward_b200", "assets")
+MODEL = os.path.join(ASSETS, "bmirobot_model.bin")
+HULLS = os.path.join(ASSETS, "bmirobot_hulls.bin")
+OUT = os.path.join(ASSETS, "bmirobot_selfcol.bin")
+GEOM = os.path.join(ROOT, "tools", "geom")
+LIB = os.path.join(GEOM, "_build", "libpairtable.so")
+SOURCES = [os.path.join(GEOM, "pair_table.c"), os.path.join(GEOM, "convex_epa.h"), os.path.join(ROOT, "include", "bmi_model.h")]
 MAGIC = 20261017.0
 HDR, DESC = 8, 16
 FAR = 0.012          # nodes whose cores are farther apart than this hold the "far" sentinel
@@ -37,42 +45,56 @@ FAR = 0.012          # nodes whose cores are farther apart than this hold the "f
 PAIRS = [(0, 2, 0, 1, 2.0), (3, 5, 3, 4, 1.0), (5, 7, 5, 6, 1.0), (8, 9, 7, 8, 1.0)]
 
 
-def _env():
-    from oracle.physics_oracle import OracleEnv, _p
-    e = OracleEnv(0)
-    e.lib.bmo_pair_query.restype = None
-    e.lib.bmo_pair_query.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
-    return e, _p
+def build_lib():
+    """gcc the sampler (same floating-point flags as every other CPU build of the repo: no contraction)"""
+    if os.path.exists(LIB) and all(os.path.getmtime(f) <= os.path.getmtime(LIB) for f in SOURCES):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    subprocess.run([os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-std=c11", "-ffp-contract=off", "-D_GNU_SOURCE", "-shared",
+                    "-o", LIB, SOURCES[0], "-lm"], check=True)
+    return LIB
+
+
+def load_hulls(path=HULLS):
+    """[(link index or -1, friction, vertices float64 (nv, 3))] of assets/bmirobot_hulls.bin"""
+    h = np.fromfile(path, dtype="<f4")
+    out, o = [], 1
+    for _ in range(int(h[0])):
+        nv = int(h[o + 2])
+        out.append((int(h[o]), float(h[o + 1]), np.ascontiguousarray(h[o + 3:o + 3 + 3 * nv].astype(np.float64).reshape(nv, 3))))
+        o += 3 + 3 * nv
+    return out
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
 
 
 def _rows(args):
     (a, b, ja, jb), qa_vals, qb_vals = args
-    e, _p = _env()
+    lib = ctypes.CDLL(build_lib())
+    lib.pt_bake_rows.restype = None
+    lib.pt_bake_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                 ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+    blob = np.fromfile(MODEL, dtype="<f4")
+    hulls = load_hulls()
+    (la, _, va), (lb, _, vb) = hulls[a], hulls[b]
+    qa_vals, qb_vals = np.ascontiguousarray(qa_vals, np.float64), np.ascontiguousarray(qb_vals, np.float64)
     out = np.zeros((len(qa_vals), len(qb_vals), 8), np.float32)
-    q = np.zeros(9)
-    tmp = np.zeros(8, np.float32)
-    for i, qa in enumerate(qa_vals):
-        for j, qb in enumerate(qb_vals):
-            q[:] = 0
-            q[ja], q[jb] = qa, qb
-            e.lib.bmo_pair_query(e.h, a, b, _p(q), FAR, _p(tmp))
-            out[i, j] = tmp
+    lib.pt_bake_rows(_p(blob), _p(va), len(va), la, _p(vb), len(vb), lb, ja, jb, _p(qa_vals), len(qa_vals), _p(qb_vals),
+                     len(qb_vals), FAR, _p(out))
     return out
 
 
 def bake(h0=0.005, procs=None, out_path=OUT, quiet=False):
-    e, _ = _env()
-    blob = e.blob
+    build_lib()
+    blob = np.fromfile(MODEL, dtype="<f4")
     links_off, stride = int(blob[4]), 32
     lo = [float(blob[links_off + stride * i + 16]) for i in range(9)]
     hi = [float(blob[links_off + stride * i + 17]) for i in range(9)]
-    hulls = e.hulls
-    mu, o = [], 1
-    link_of = []
-    for _i in range(int(hulls[0])):
-        link_of.append(int(hulls[o]))
-        mu.append(float(hulls[o + 1]))
-        o += 3 + 3 * int(hulls[o + 2])
+    hulls = load_hulls()
+    link_of, mu = [h[0] for h in hulls], [h[1] for h in hulls]
     procs = procs or os.cpu_count() or 1
     descs, tables, off = [], [], HDR + DESC * len(PAIRS)
     with Pool(procs) as pool:
