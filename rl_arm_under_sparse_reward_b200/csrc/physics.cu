@@ -52,6 +52,21 @@ constexpr int kContactUnroll = BMI_CONTACT_UNROLL;
 #ifndef BMI_SOLVE_SINGLE_VARIANT
 #define BMI_SOLVE_SINGLE_VARIANT 0
 #endif
+// Block island (block-table rows while no arm link touches the block), see substep_solve (b), (c):
+#ifndef BMI_BLK_WARMSTART
+#define BMI_BLK_WARMSTART 0   // 1: start its rows from the previous sub-step's impulses.  OFF: four corner contacts are statically
+                              // indeterminate, PGS then converges to a different point than Bullet's cold start and a sliding /
+                              // spinning block decays differently (measured: 0.59 rad/s after one env-step at 5.8 rad/s)
+#endif
+#ifndef BMI_BLK_FREEZE
+#define BMI_BLK_FREEZE 1      // stop sweeping its rows once converged (0: sweep them to the end like Bullet: 25 % slower)
+#endif
+#ifndef BMI_BLK_FREEZE_REST
+#define BMI_BLK_FREEZE_REST 1e-2f   // "converged" = squared row-velocity change below this fraction of Bullet's threshold ...
+#endif
+#ifndef BMI_BLK_FREEZE_MOVING
+#define BMI_BLK_FREEZE_MOVING 1e-4f // ... 100x tighter while the block moves (> 1 mm/s): there the truncation error accumulates
+#endif
 #ifndef BMI_MOTOR_UNROLL
 #define BMI_MOTOR_UNROLL 3
 #endif
@@ -1017,8 +1032,9 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   //     iteration of lag.  n_c iterations with K-fold steps on those rows followed by `tail` plain ones land on the same
   //     point: K n_c + tail = MP_SOLVER_ITERS equivalent iterations.
   // (b) Block island: while no arm link touches the block, the block-table rows form a separate island that converges
-  //     in 20-30 iterations; once its residual is below the threshold its rows are skipped (Bullet keeps sweeping them
-  //     with impulse changes below 3e-4 x the row diagonal).
+  //     in 20-50 iterations; once its residual is below the threshold its rows are skipped (Bullet keeps sweeping them
+  //     with impulse changes below 3e-4 x the row diagonal).  The threshold is 100x below Bullet's for a block at rest
+  //     and 10 000x below while the block moves (there a truncated solve biases the friction every sub-step).
   unsigned self_mask = 0u, blk_mask = 0u, armblk_mask = 0u;   // per contact slot
   {
     const int info = lane < nc ? s.cinfo[lane] : 0;
@@ -1039,10 +1055,15 @@ __device__ __noinline__ void substep_solve(Smem& s, const EnvParams& ep, int lan
   const bool blk_lane = own_ct && ((blk_mask >> myc) & 1u);
   const bool blk_island = armblk_mask == 0u && blk_mask != 0u;
   unsigned skip_mask = 0u;      // contact slots whose rows are no longer swept
-  // (c) Warm start of the block island: its converged solution does not depend on the starting point, so the rows start
-  //     from the previous sub-step's impulses (same block vertex on the table) and are done after 1-3 sweeps instead of
-  //     ~45 from zero.  Only while the island is decoupled from the arm; Bullet's cold start otherwise.
-  if (blk_island) {
+  // freeze threshold of the island: tangential + angular speed of the block before the solve (warp-uniform)
+  const float blk_speed2 = s.u[9] * s.u[9] + s.u[10] * s.u[10] +
+                           9e-4f * (s.u[12] * s.u[12] + s.u[13] * s.u[13] + s.u[14] * s.u[14]);   // 3 cm lever arm
+  const float blk_freeze = (blk_speed2 > 1e-6f ? BMI_BLK_FREEZE_MOVING : BMI_BLK_FREEZE_REST) * thresh;
+  // (c) Warm start of the block island (compile-time option, OFF): starting its rows from the previous sub-step's impulses
+  //     ends the island after 1-3 sweeps instead of ~45, but four corner contacts are statically indeterminate and PGS then
+  //     converges to a different point than from Bullet's cold start (the multibody solver does not warm-start): a sliding
+  //     or spinning block decayed measurably differently from the oracle.  Cold start costs ~1 % of the rollout.
+  if (blk_island && BMI_BLK_WARMSTART) {
     const unsigned ids = s.blk_ids;
     if (blk_lane) {
       const int vid = c_vid(s.cinfo[myc]);
@@ -1164,7 +1185,7 @@ _Pragma("unroll 1") \
       } \
       if (want_blk) { \
         const float rb = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(blk_lane ? rl : 0.f))); \
-        if (rb <= 1e-2f * thresh) { skip_mask = blk_mask; active &= ~blk_mask; } \
+        if (BMI_BLK_FREEZE && rb <= blk_freeze) { skip_mask = blk_mask; active &= ~blk_mask; } \
       } \
     } \
   }

@@ -37,4 +37,20 @@ for e in np.argsort(-errs)[:4]:
     ds = st2[e] - states[e]
     ks = np.argsort(-np.abs(ds))[:8]
     print("   state dims %s diffs %s" % (ks, ds[ks]))
+# sensitivity of the ORACLE itself at those states: the same step from states whose joint angles differ by +-1e-6 rad
+# (a few float32 ulps): where the kernel's outliers sit on a discontinuity (contact feature switch), the oracle moves as much
+print("env  kernel-vs-oracle  oracle-vs-perturbed-oracle (max over 4 perturbations)")
+rs = np.random.RandomState(1)
+for e in np.argsort(-errs)[:10].tolist() + np.argsort(errs)[:3].tolist():
+    sens = 0.0
+    for k in range(4):
+        o = OracleEnv(0 if task == "push" else 1)
+        o.kernel_mode()
+        o.reset(init[e])
+        s2 = st[e].copy()
+        s2[:9] += rs.uniform(-1e-6, 1e-6, 9)
+        o.set_state(s2)
+        w2, _, _, _ = o.step(act[e])
+        sens = max(sens, np.abs(w2 - wants[e]).max())
+    print("%3d  %.3e  %.3e" % (e, errs[e], sens))
 print("median %.2e" % np.median(errs))
