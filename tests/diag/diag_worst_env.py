@@ -1,5 +1,5 @@
-"""Which observation components carry the worst kernel-vs-oracle one-step errors (tests/test_gpu_physics.py scenario)?
-    python tests/diag/diag_worst_env.py [push|pick]"""
+"""Which observation components carry the worst kernel-vs-oracle one-step errors (tests/test_gpu_physics.py scenarios)?
+    python tests/diag/diag_worst_env.py [push|pick] [random|contact]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -7,15 +7,31 @@ from rl_arm_under_sparse_reward_b200.bmirobot_env.vec_env import BmiVecEnv
 from oracle.physics_oracle import OracleEnv
 
 task = sys.argv[1] if len(sys.argv) > 1 else "push"
+scenario = sys.argv[2] if len(sys.argv) > 2 else "random"      # random | contact (hand pressed onto the table next to the block)
 n = 64
-env = BmiVecEnv(n, task=task, seed=7)
-env.reset()
-rng = np.random.RandomState(0)
-for t in range(5):
-    env.step(torch.as_tensor(rng.uniform(-0.3, 0.3, (n, 4)).astype(np.float32)).cuda())
+if scenario == "contact":
+    env = BmiVecEnv(n, task=task, seed=21)
+    obs, ag, g = env.reset()
+    dev = obs.device
+    rng = np.random.RandomState(3)
+    for t in range(30):
+        grip, blk = obs[:, :3], obs[:, 12:15]
+        tgt = blk + torch.tensor([0.0, 0.0, 0.01], device=dev)
+        a = torch.cat([(tgt - grip).clamp(-0.2, 0.2), torch.zeros(n, 1, device=dev)], 1)
+        a[:, 2] -= 0.05 * (t > 15)
+        a[:, :2] += torch.as_tensor(rng.uniform(-0.05, 0.05, (n, 2)).astype(np.float32), device=dev)
+        obs, ag, _, _ = env.step(a.float().contiguous())
+    act = rng.uniform(-0.3, 0.3, (n, 4)).astype(np.float32)
+    act[:, 2] = -np.abs(act[:, 2])
+else:
+    env = BmiVecEnv(n, task=task, seed=7)
+    env.reset()
+    rng = np.random.RandomState(0)
+    for t in range(5):
+        env.step(torch.as_tensor(rng.uniform(-0.3, 0.3, (n, 4)).astype(np.float32)).cuda())
+    act = rng.uniform(-0.5, 0.5, (n, 4)).astype(np.float32)
 st = env.get_state().cpu().numpy().astype(np.float64)
 init = env.init.cpu().numpy().astype(np.float64)
-act = rng.uniform(-0.5, 0.5, (n, 4)).astype(np.float32)
 obs, ag, r, s = env.step(torch.as_tensor(act).cuda())
 got = obs.cpu().numpy()
 st2 = env.get_state().cpu().numpy().astype(np.float64)
@@ -49,6 +65,7 @@ for e in np.argsort(-errs)[:10].tolist() + np.argsort(errs)[:3].tolist():
         o.reset(init[e])
         s2 = st[e].copy()
         s2[:9] += rs.uniform(-1e-6, 1e-6, 9)
+        s2[27:30] += rs.uniform(-1e-6, 1e-6, 3)          # and the block position by a micrometre
         o.set_state(s2)
         w2, _, _, _ = o.step(act[e])
         sens = max(sens, np.abs(w2 - wants[e]).max())

@@ -67,6 +67,32 @@ def _oracle_rollout(task, init, acts, state=None):
     return out, o.get_state()
 
 
+def _oracle_sensitivity(task, init, st, act, ref, n_pert=4, seed=1):
+    """max |oracle(step from st + 1e-6 perturbation) - oracle(step from st)|: large where st sits on a discontinuity"""
+    rs = np.random.RandomState(seed)
+    sens = 0.0
+    for _ in range(n_pert):
+        o = _kernel_oracle(0 if task == "push" else 1)
+        o.reset(init)
+        s2 = st.copy()
+        s2[:9] += rs.uniform(-1e-6, 1e-6, 9)             # joint angles: a few float32 ulps
+        s2[27:30] += rs.uniform(-1e-6, 1e-6, 3)          # block position: a micrometre
+        o.set_state(s2)
+        w2, _, _, _ = o.step(act)
+        sens = max(sens, float(np.abs(w2 - ref).max()))
+    return sens
+
+
+def _unexplained_outliers(task, init, st, act, want, errs, tol):
+    """envs whose kernel-vs-oracle error exceeds tol although the oracle itself is smooth there (error > 10 x sensitivity)"""
+    bad = []
+    for e in np.nonzero(errs > tol)[0]:
+        sens = _oracle_sensitivity(task, init[e], st[e], act[e], want[e])
+        if errs[e] > 10.0 * sens:
+            bad.append((int(e), float(errs[e]), sens))
+    return bad
+
+
 @pytest.mark.parametrize("task", ["push", "pick"])
 def test_single_step_vs_oracle_from_random_states(task):
     n = 64
@@ -81,10 +107,11 @@ def test_single_step_vs_oracle_from_random_states(task):
     act = rng.uniform(-0.5, 0.5, (n, 4)).astype(np.float32)
     obs, ag, r, s = env.step(torch.as_tensor(act).cuda())
     got = obs.cpu().numpy()
-    errs = []
+    errs, wants = [], []
     for e in range(n):
         (res,), _ = _oracle_rollout(task, init[e], [act[e]], state=st[e])
         errs.append(np.abs(got[e] - res[0]).max())
+        wants.append(res[0])
         assert r[e].item() == res[1] and s[e].item() == res[2] or errs[-1] > 1e-4
     errs = np.array(errs)
     # measured: median 1e-4, p90 2e-4 .. 3e-4, 95 % of the envs within 2e-3; the rest sit on discontinuities -- the wrist
@@ -94,6 +121,10 @@ def test_single_step_vs_oracle_from_random_states(task):
     print("one step vs oracle (%s): median %.2e, p90 %.2e, max %.2e" % (task, np.median(errs), np.percentile(errs, 90), errs.max()))
     assert np.mean(errs <= 2e-3) >= 0.85, np.sort(errs)[-8:]
     assert np.median(errs) <= 2e-4, np.median(errs)
+    # ... and the exempt envs are justified one by one: an error above 2e-3 is only accepted where the oracle's own answer
+    # moves by at least a tenth of it under a 1e-6 perturbation of the state (at most two unexplained envs of 64)
+    bad = _unexplained_outliers(task, init, st, act, wants, errs, 2e-3)
+    assert len(bad) <= 2, bad
 
 
 def test_single_step_vs_oracle_from_contact_rich_states():
@@ -120,7 +151,7 @@ def test_single_step_vs_oracle_from_contact_rich_states():
     obs, _, r, s = env.step(torch.as_tensor(act).cuda())
     got = obs.cpu().numpy()
     assert np.isfinite(got).all()
-    errs, ncs = [], []
+    errs, ncs, wants = [], [], []
     for e in range(n):
         o = _kernel_oracle(0)
         o.reset(init[e])
@@ -128,11 +159,14 @@ def test_single_step_vs_oracle_from_contact_rich_states():
         want, _, _, _ = o.step(act[e])
         ncs.append(o.stats()[2])
         errs.append(np.abs(got[e] - want).max())
+        wants.append(want)
     errs, ncs = np.array(errs), np.array(ncs)
     assert (ncs > 4).mean() > 0.3, ncs          # the scenario really is contact rich (more than the 4 block-table contacts)
     print("one step vs oracle (contact rich): median %.2e, p90 %.2e, max %.2e" % (np.median(errs), np.percentile(errs, 90), errs.max()))
     assert np.mean(errs <= 5e-3) >= 0.85, np.sort(errs)[-12:]
     assert np.median(errs) <= 5e-4, np.median(errs)
+    bad = _unexplained_outliers("push", init, st, act, wants, errs, 5e-3)    # see the random-state test
+    assert len(bad) <= 2, bad
 
 
 def test_arm_trajectory_of_reference_episode0(golden_dir):
