@@ -1201,7 +1201,7 @@ _Pragma("unroll 1") \
 #undef BMI_JOINT_EVENT
   PROF_CNT(s.prof_e, 7, it);
   __syncwarp();   // the warm-start reads above are ordered before the stores below (shuffles are not memory barriers)
-  {  // impulses of the block island for the next sub-step's warm start
+  if (BMI_BLK_WARMSTART) {  // impulses of the block island for the next sub-step's warm start
     const int slot = __popc(blk_mask & ((1u << (myc & 31)) - 1u));   // rank of this lane's contact among the block-table contacts
     if (blk_island && blk_lane && slot < 4) { s.blk_lam[3 * slot] = lam0; s.blk_lam[3 * slot + 1] = lam1; s.blk_lam[3 * slot + 2] = lam2; }
     unsigned idb = blk_island && blk_lane && slot < 4 ? ((unsigned)c_vid(s.cinfo[myc]) << (8 * slot)) | ~(0xffu << (8 * slot)) : 0xffffffffu;
