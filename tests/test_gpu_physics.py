@@ -299,7 +299,7 @@ def test_single_step_vs_oracle_from_gripping_states():
     act = pick_controller(81, obs, g)
     got = env.step(act)[0].cpu().numpy()
     act = act.cpu().numpy()
-    errs, grip = [], []
+    errs, grip, wants = [], [], []
     for e in range(n):
         o = _kernel_oracle(1)
         o.reset(init[e])
@@ -311,11 +311,16 @@ def test_single_step_vs_oracle_from_gripping_states():
         want, _, _, _ = o.step(act[e])
         grip.append(e)
         errs.append(np.abs(got[e] - want).max())
+        wants.append(want)
     errs = np.array(errs)
     print("gripping states: %d of %d envs; one-step error median %.2e p90 %.2e" % (len(grip), n, np.median(errs), np.percentile(errs, 90)))
     assert len(grip) >= 10, len(grip)
     assert np.mean(errs <= 5e-3) >= 0.8, np.sort(errs)[-12:]
     assert np.median(errs) <= 1e-3, np.median(errs)
+    # the exempt envs sit on discontinuities of the oracle itself (see test_single_step_vs_oracle_from_random_states)
+    bad = _unexplained_outliers("pick", init[grip], st[grip], act[grip], wants, errs, 5e-3)
+    print("gripping states: %d envs beyond 5e-3, unexplained by the oracle's own sensitivity: %s" % (int((errs > 5e-3).sum()), bad))
+    assert len(bad) <= 3, bad
 
 
 def test_scripted_pick_success_rate():
