@@ -39,10 +39,10 @@ ALGO_BYTES_PER_ENV_STEP = 412          # state in+out 2x136 + actio
 NCU_DRAM_BYTES_PER_LAUNCH = 108596736  # 17.92 MB read + 90.68 MB written
 # sm__warps_active / smsp__issue_active / FMA pipe of the same capture; numeric so that the roofline object says what bounds
 # this FP32-issue kernel (the HBM fraction cannot): 28 of 64 warp slots resident by design (shared memory), issue slots 75 % busy
-# (T = 100 capture; the final kernel's cheaper motor / contact-normal rows were re-captured at T = 10 only: 6.6 % fewer
-# instructions than the T = 10 capture of the same table, hence 36.6 k -> 34.2 k per env sub-step)
+# (T = 100 capture.  The final kernel -- cheaper motor / contact-normal rows, block island started cold -- was re-captured at
+# T = 10 only: 3.156e10 warp instructions against 3.153e10 for the T = 10 capture of the same table, i.e. the same 36.6 k)
 NCU_ROLLOUT = {"warps_active_pct": 42.2, "issue_slot_util_pct": 75.3, "fma_pipe_pct": 28.6, "lsu_pipe_pct": 60.6,
-               "warp_instructions_per_env_substep": 34200}
+               "warp_instructions_per_env_substep": 36600}
 METRIC = "env-steps/s (push, 4096 envs) at 1/2/4/8 B200 vs CPU PyBullet+MPI"
 
 
