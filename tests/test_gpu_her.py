@@ -205,6 +205,36 @@ def test_fused_inputs_large_ragged_batch_bit_exact():
             assert bool((tail[B:] == 7.0).all())
 
 
+def test_fused_inputs_wide_observation_fallback_bit_exact():
+    """obs_dim + goal_dim > 32 takes the tiled sampler (her_inputs_kernel) instead of the lane-per-element one: same bit-exact
+    contract, both tile sizes (batch <= 8192 and above)."""
+    _lib, _, _ = _mods()
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(4)
+    E, T, Do, Dg, Da = 40, 50, 40, 5, 6
+    buf = {"obs": rng.standard_normal((E, T + 1, Do)), "ag": rng.standard_normal((E, T + 1, Dg)) * 0.05,
+           "g": rng.standard_normal((E, T, Dg)) * 0.05, "actions": rng.uniform(-1, 1, (E, T, Da))}
+    on, gn = lo.Normalizer(Do, clip=5), lo.Normalizer(Dg, clip=5)
+    on.mean, on.std = (rng.standard_normal(Do) * 0.2).astype(np.float32), rng.uniform(0.05, 1.5, Do).astype(np.float32)
+    gn.mean, gn.std = (rng.standard_normal(Dg) * 0.01).astype(np.float32), rng.uniform(0.01, 0.1, Dg).astype(np.float32)
+    for B in (777, 9001):
+        np.random.seed(B)
+        draws = lo.her_draw_numpy(E, T, B)
+        x, xn, a, r = lo.network_inputs(lo.her_sample_with_draws(buf, draws, 0.8), on, gn)
+        t = {k: torch.as_tensor(v).to(dev, torch.float64).contiguous() for k, v in buf.items()}
+        eps = _lib.Episodes(_lib.ptr(t["obs"]), _lib.ptr(t["ag"]), _lib.ptr(t["g"]), _lib.ptr(t["actions"]), E, T, Do, Dg, Da,
+                            _lib.dtype_code(torch.float64), 0)
+        d = [torch.as_tensor(v).to(dev) for v in draws]
+        mk = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        X, XN, A, Rr = mk(B, Do + Dg), mk(B, Do + Dg), mk(B, Da), mk(B)
+        st = [torch.as_tensor(v).to(dev) for v in (on.mean, on.std, gn.mean, gn.std)]
+        _lib.call("bmi_her_sample_inputs", ctypes.byref(eps), E, _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]),
+                  B, 0.8, 0.05, 200.0, 5.0, _lib.ptr(st[0]), _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]), _lib.ptr(X),
+                  _lib.ptr(XN), _lib.ptr(A), _lib.ptr(Rr), _lib.stream_ptr())
+        assert np.array_equal(X.cpu().numpy(), x) and np.array_equal(XN.cpu().numpy(), xn), B
+        assert np.array_equal(A.cpu().numpy(), a) and np.array_equal(Rr.cpu().numpy(), r[:, 0]), B
+
+
 def test_device_philox_draws_match_oracle():
     _lib, _, _ = _mods()
     dev = torch.device("cuda")
