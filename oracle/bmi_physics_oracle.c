@@ -7,12 +7,14 @@
  * to PyBullet 3.1.7 (README.md:10; Bullet btMultiBodyDynamicsWorld + BussIK), which is neither
  * in the reference tree nor installable here.  This file restates the published algorithm
  * (Featherstone forward dynamics, velocity-level MLCP solved by projected Gauss-Seidel with
- * Bullet's row set-up, DLS inverse kinematics) and is pinned only on what the reference's own
- * recorded trajectories (bmirobot_1000_*_demo.npz) determine: reset pose, block drop/settle
- * transient (contact ERP 0.08, slop 1e-5, matched to 1e-6) and sliding friction.  The arm's
- * permanent self-contact needs Bullet's GJK/EPA manifolds and is NOT modelled, so
- * the arm trajectory of episode 0 is reproduced only qualitatively (tests/test_oracle_physics.py
- * records the measured gap).
+ * Bullet's row set-up and row order, GJK / EPA self-collision of the arm's convex hulls with
+ * Bullet's same-multibody row diagonal, DLS inverse kinematics) and is pinned on what the
+ * reference's own recorded trajectories (bmirobot_1000_*_demo.npz) determine: reset pose, block
+ * drop / settle transient (contact ERP 0.08, slop 1e-5, matched to 1e-6), sliding friction, the
+ * 10-step arm trajectory of the fresh-process episode 0 (EE within 0.9 mm after step 1, 14.3 mm
+ * after step 10; wrist hold angle and elbow stall of the permanent self-contacts)
+ * and the open-loop replay of whole recorded push / pick episodes (tests/test_oracle_physics.py,
+ * profiles/r02_reference_replay.md).
  *
  * Reference call sites restated (paths relative to the reference tree):
  *   bmirobot_env/bmirobot_env_push_F.py:92-108   step: clip, action[3]=0, IK+motors, 20 sub-steps
