@@ -1,6 +1,7 @@
-// DDPG learner: actor/critic MLP forward + backward as cuBLASLt fp32 GEMMs (bias+ReLU fused
-// in the GEMM epilogue), fused loss / head / dReLU+bias-grad kernels, multi-tensor Adam on
-// flat parameter buffers, Polyak averaging.
+// DDPG learner: the update as two hand-written kernels (ddpg_fused.cuh: the default for the reference's shapes) or, for
+// other hidden widths / BMI_DDPG_CUBLAS=1, as a chain of cuBLASLt fp32 GEMMs (bias+ReLU fused in the GEMM epilogue) with fused
+// loss / head / dReLU+bias-grad kernels; the policy forward (bmi_ddpg_act); multi-tensor Adam on flat parameter buffers, alone
+// or fused with the gradient sum over ranks through NVLink peer memory; Polyak averaging.
 //
 // Reference behaviour restated (paths relative to the reference tree):
 //   models.py:11-44            actor / critic

@@ -3,8 +3,8 @@
 // Reference behaviour restated here (paths relative to the reference tree):
 //   replay_buffer.py:32-43   store_episode        -> store_kernel
 //   bmirobot_env_push_F.py:20-23,84-90  reward    -> reward_kernel / inside her kernels
-//   her.py:13-41             sample_her_transitions -> her_gather_kernel / her_inputs_kernel
-//   ddpg_agent.py:229-248    clip + normalise + concat + f32 cast -> her_inputs_kernel
+//   her.py:13-41             sample_her_transitions -> her_gather_kernel / her_inputs_lane_kernel (wide layouts: her_inputs_kernel)
+//   ddpg_agent.py:229-248    clip + normalise + concat + f32 cast -> her_inputs_lane_kernel
 //
 // Bit-exactness: every float64 operation that numpy performs is issued with the
 // round-to-nearest intrinsics (__dadd_rn/__dmul_rn/...) so nvcc cannot contract them

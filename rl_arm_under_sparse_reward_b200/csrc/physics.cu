@@ -12,7 +12,8 @@
 //
 // Per sub-step: forward kinematics -> mass matrix by composite rigid bodies + bias by one
 // Newton-Euler pass (joint_space_dynamics) -> register-resident Cholesky -> M^-1 -> unconstrained
-// velocities -> contact generation (lane = vertex, bounding-sphere broadphase) -> constraint rows
+// velocities -> contact generation (arm self-collision from the baked two-joint pair tables, bmirobot.py:58 flags=9; block /
+// table / arm contacts: lane = vertex, bounding-sphere broadphase) -> constraint rows
 // (lane = row) and their coupling table -> projected Gauss-Seidel in constraint space (lane = joint /
 // block velocity component / contact; one shuffle per row update, substep_solve) -> semi-implicit
 // Euler.  fp32 throughout, no tensor cores.
