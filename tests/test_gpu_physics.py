@@ -120,6 +120,7 @@ def test_single_step_vs_oracle_from_random_states(task):
     # 1e-6 rad (tests/diag/diag_worst_env.py prints both columns): discrete events, not drift
     print("one step vs oracle (%s): median %.2e, p90 %.2e, max %.2e" % (task, np.median(errs), np.percentile(errs, 90), errs.max()))
     assert np.mean(errs <= 2e-3) >= 0.85, np.sort(errs)[-8:]
+    assert np.mean(errs <= 1e-3) >= 0.90, np.sort(errs)[-8:]     # north_star's 1e-3 (observations are O(0.1 .. 1)): measured 95 %
     assert np.median(errs) <= 2e-4, np.median(errs)
     # ... and the exempt envs are justified one by one: an error above 2e-3 is only accepted where the oracle's own answer
     # moves by at least a tenth of it under a 1e-6 perturbation of the state (at most two unexplained envs of 64)
